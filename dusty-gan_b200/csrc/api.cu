@@ -1,0 +1,74 @@
+// Library-wide plumbing of libdustyb200: error strings, launch accounting, device check and the
+// FP32 peak probe that bench.py uses as the measured FFMA roofline denominator.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace dusty {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int fail_cuda(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+
+int fail_arg(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int check_device() {
+  static thread_local int checked_dev = -1;
+  int dev = 0;
+  DUSTY_CUDA(cudaGetDevice(&dev));
+  if (dev == checked_dev) return 0;
+  int major = 0;
+  DUSTY_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail_arg(DUSTY_EARCH, "device %d has compute capability %d.x; this library is sm_100a only", dev, major);
+  checked_dev = dev;
+  return 0;
+}
+
+// 8 independent accumulators x 512 rounds = 4096 FFMA per thread per iteration; operands never
+// leave registers, so this is the FMA-pipe ceiling as an FFMA-only kernel sees it.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float* sink) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+    #pragma unroll 64
+    for (int k = 0; k < 512; ++k) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456f) sink[0] = s;   // practically never true: keeps the chain alive without traffic
+}
+
+}  // namespace dusty
+
+using namespace dusty;
+
+extern "C" int dusty_abi_version(void) { return DUSTY_B200_ABI_VERSION; }
+extern "C" const char* dusty_last_error_string(void) { return g_err; }
+extern "C" uint64_t dusty_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int dusty_probe_fp32_peak(int iters, float* sink, double* flops_out, void* stream) {
+  if (iters <= 0 || !sink) return fail_arg(DUSTY_EINVAL, "probe_fp32_peak: bad arguments");
+  if (int rc = check_device()) return rc;
+  const int grid = kNumSMs * 8;
+  fp32_peak_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, sink);
+  DUSTY_AFTER_LAUNCH("fp32_peak_kernel");
+  if (flops_out) *flops_out = 2.0 * 4096.0 * iters * 256.0 * grid;
+  return 0;
+}

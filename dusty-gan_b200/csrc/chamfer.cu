@@ -1,0 +1,469 @@
+// Chamfer nearest-neighbour kernels for sm_100a.
+//
+// Replaces ChamferDistanceKernel (reference utils/metrics/distance/cd/chamfer_distance.cu:6-131),
+// its launcher (:133-146) and the Python double loop _pairwise_distance that calls it once per row
+// and 512-column block (reference utils/metrics/cov_mmd_1nna.py:24-51).
+//
+// One kernel, two front ends:
+//   * batch  -- dusty_chamfer_forward: per-point (dist, idx) in both directions for b cloud pairs
+//   * matrix -- dusty_chamfer_matrix : one CTA per matrix entry (cloud i of A, cloud j of B), both
+//               directions, reduced on chip to M[i,j] = mean(dist1) + mean(dist2)  (compute_cd,
+//               reference cov_mmd_1nna.py:19-21)
+//
+// Arithmetic. A directed search keeps R "row" points per thread in registers and streams the
+// other cloud through shared memory in 2048-point tiles (1-D TMA bulk copies, double buffered on
+// two mbarriers). Tiles are in *scan format*: for points 2q, 2q+1 two float4 {x0,x1,y0,y1}
+// {z0,z1,n0,n1} with n = |p|^2, so one LDS.128 pair feeds packed FFMA2 directly.
+//   search:  s(a,b) = |b|^2 - 2 a.b  as 3 FFMA2 per two candidates + one 3-input FMNMX, and per
+//            32-candidate chunk one compare/select that remembers which chunk holds the minimum;
+//   exact :  the winning chunk (1.6 % of the tile) is re-evaluated in the reference's rounding,
+//            d = fma(dz,dz,fma(dx,dx,dy*dy)) on differences, and the minimum of those is the
+//            result. Every reported distance is therefore a value the reference kernel would have
+//            computed for some candidate, and it is the reference's minimum unless two candidates
+//            in different chunks are closer to each other than the search's rounding error
+//            (~2^-23 (|a|^2+|b|^2)), in which case it exceeds the minimum by at most that much.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dusty {
+namespace chamfer {
+
+constexpr int TPB = 256;
+constexpr int TILE = 2048;            // scan points per shared-memory tile (= float4 per tile)
+constexpr int CHUNK = 32;             // candidates per search chunk
+constexpr int PAIRS = CHUNK / 2;
+constexpr int SMEM_BYTES = 2 * TILE * 16;
+
+struct Params {
+  const float4* scanX;      // scan-format clouds, X side (rows of the matrix / xyz1)
+  const float4* scanY;      // Y side (columns / xyz2)
+  long long strideX, strideY;   // float4 per cloud (= padded point count)
+  int countX, countY;       // points per cloud
+  int paddedX, paddedY;     // counts rounded up to CHUNK
+  // matrix front end
+  int row_begin, row_stride;
+  int symmetric, mirror, compact_rows;
+  float* M;
+  long long ldm;
+  // batch front end
+  float* dist1; float* dist2;
+  int* idx1; int* idx2;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+    #pragma unroll
+    for (int w = 0; w < TPB / 32; ++w) s += red[w];   // fixed order: result independent of sharding
+  }
+  return s;
+}
+
+template <int R, bool MATRIX>
+__global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* const tiles = reinterpret_cast<float4*>(smem_raw);
+  __shared__ uint64_t bars[2];
+  __shared__ double red[TPB / 32];
+
+  constexpr int RB = TPB * R;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+
+  // ---- which clouds ----
+  int ci, cj;            // cloud index on the X side and on the Y side
+  int dir_only = -1, rb_only = 0;
+  if (MATRIX) {
+    ci = p.row_begin + blockIdx.y * p.row_stride;
+    cj = blockIdx.x;
+    if (p.symmetric && cj < ci) return;
+  } else {
+    ci = cj = blockIdx.y;
+    dir_only = blockIdx.z;
+    rb_only = blockIdx.x;
+    const int nrb = ((dir_only == 0 ? p.countX : p.countY) + RB - 1) / RB;
+    if (rb_only >= nrb) return;
+  }
+  const float4* const sx = p.scanX + (long long)ci * p.strideX;
+  const float4* const sy = p.scanY + (long long)cj * p.strideY;
+
+  const int ntX = (p.paddedX + TILE - 1) / TILE, ntY = (p.paddedY + TILE - 1) / TILE;
+  const int nrbX = (p.countX + RB - 1) / RB, nrbY = (p.countY + RB - 1) / RB;
+  const int seg0 = nrbX * ntY;
+  int pos_begin, pos_end;
+  if (MATRIX) { pos_begin = 0; pos_end = seg0 + nrbY * ntX; }
+  else if (dir_only == 0) { pos_begin = rb_only * ntY; pos_end = pos_begin + ntY; }
+  else { pos_begin = seg0 + rb_only * ntX; pos_end = pos_begin + ntX; }
+
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  __syncthreads();
+
+  // tile stream: position -> (direction, row block, scan tile)
+  auto issue = [&](int pos, int buf) {
+    int dir, t;
+    if (pos < seg0) { dir = 0; t = pos % ntY; } else { dir = 1; t = (pos - seg0) % ntX; }
+    const float4* src = (dir == 0 ? sy : sx) + (long long)t * TILE;
+    const int padded = dir == 0 ? p.paddedY : p.paddedX;
+    const int npts = min(TILE, padded - t * TILE);
+    mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u);
+    bulk_g2s(tiles + buf * TILE, src, (uint32_t)npts * 16u, &bars[buf]);
+  };
+  if (tid == 0) issue(pos_begin, 0);
+
+  float nax[R], nay[R], naz[R];     // -2 * row coordinates (search operands)
+  float eb[R];                      // exact running minimum over tiles
+  int ei[R];                        // its index (batch front end only)
+  double dsum = 0.0, S0 = 0.0;
+
+  for (int pos = pos_begin; pos < pos_end; ++pos) {
+    const int it = pos - pos_begin;
+    const int buf = it & 1;
+    if (tid == 0 && pos + 1 < pos_end) issue(pos + 1, buf ^ 1);
+
+    int dir, rb, t, nt;
+    if (pos < seg0) { dir = 0; rb = pos / ntY; t = pos - rb * ntY; nt = ntY; }
+    else { dir = 1; const int q = pos - seg0; rb = q / ntX; t = q - rb * ntX; nt = ntX; }
+    const float4* const rows = dir == 0 ? sx : sy;
+    const int rowcount = dir == 0 ? p.countX : p.countY;
+    const int scanpadded = dir == 0 ? p.paddedY : p.paddedX;
+
+    if (t == 0) {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = rb * RB + r * TPB + tid;
+        const int rr = row < rowcount ? row : 0;
+        const float4 a0 = rows[(rr >> 1) * 2], a1 = rows[(rr >> 1) * 2 + 1];
+        const bool hi = rr & 1;
+        nax[r] = -2.0f * (hi ? a0.y : a0.x);
+        nay[r] = -2.0f * (hi ? a0.w : a0.z);
+        naz[r] = -2.0f * (hi ? a1.y : a1.x);
+        eb[r] = __int_as_float(0x7f800000);
+        ei[r] = 0;
+      }
+    }
+
+    mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+    const float4* const tp = tiles + buf * TILE;
+    const int nch = min(TILE, scanpadded - t * TILE) / CHUNK;
+
+    // ---- search: which chunk of this tile holds the smallest |b|^2 - 2 a.b ----
+    float cur[R];
+    int cid[R];
+    #pragma unroll
+    for (int r = 0; r < R; ++r) { cur[r] = __int_as_float(0x7f800000); cid[r] = 0; }
+    for (int c = 0; c < nch; ++c) {
+      const float4* cp = tp + c * CHUNK;
+      float cm[R];
+      #pragma unroll
+      for (int k = 0; k < PAIRS; ++k) {
+        const float4 q0 = cp[2 * k], q1 = cp[2 * k + 1];
+        const f32x2 bx = pack2(q0.x, q0.y), by = pack2(q0.z, q0.w);
+        const f32x2 bz = pack2(q1.x, q1.y), bn = pack2(q1.z, q1.w);
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+          f32x2 s = fma2(pack2(naz[r], naz[r]), bz, bn);
+          s = fma2(pack2(nay[r], nay[r]), by, s);
+          s = fma2(pack2(nax[r], nax[r]), bx, s);
+          float lo, hi;
+          unpack2(s, lo, hi);
+          cm[r] = (k == 0) ? fminf(lo, hi) : min3(cm[r], lo, hi);
+        }
+      }
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool better = cm[r] < cur[r];     // strict: the earliest chunk keeps bit-equal minima
+        cur[r] = better ? cm[r] : cur[r];
+        cid[r] = better ? c : cid[r];
+      }
+    }
+
+    // ---- exact: re-evaluate the winning chunk with the reference's rounding ----
+    constexpr int G = R < 4 ? R : 4;
+    #pragma unroll
+    for (int g = 0; g < R; g += G) {
+      float e[G];
+      int eidx[G];
+      f32x2 ax2[G], ay2[G], az2[G];
+      const float4* cp[G];
+      #pragma unroll
+      for (int r = 0; r < G; ++r) {
+        e[r] = __int_as_float(0x7f800000);
+        eidx[r] = 0x7fffffff;
+        const float x = -0.5f * nax[g + r], y = -0.5f * nay[g + r], z = -0.5f * naz[g + r];
+        ax2[r] = pack2(x, x); ay2[r] = pack2(y, y); az2[r] = pack2(z, z);
+        cp[r] = tp + cid[g + r] * CHUNK;
+      }
+      #pragma unroll 4
+      for (int k = 0; k < PAIRS; ++k) {
+        const int kk = (k + lane) & (PAIRS - 1);   // lanes start on different banks
+        #pragma unroll
+        for (int r = 0; r < G; ++r) {
+          const float4 q0 = cp[r][2 * kk], q1 = cp[r][2 * kk + 1];
+          const f32x2 dx = sub2(pack2(q0.x, q0.y), ax2[r]);
+          const f32x2 dy = sub2(pack2(q0.z, q0.w), ay2[r]);
+          const f32x2 dz = sub2(pack2(q1.x, q1.y), az2[r]);
+          const f32x2 d = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+          float lo, hi;
+          unpack2(d, lo, hi);
+          if (MATRIX) {
+            e[r] = min3(e[r], lo, hi);
+          } else {
+            const int i0 = t * TILE + cid[g + r] * CHUNK + 2 * kk;
+            if (lo < e[r] || (lo == e[r] && i0 < eidx[r])) { e[r] = lo; eidx[r] = i0; }
+            if (hi < e[r] || (hi == e[r] && i0 + 1 < eidx[r])) { e[r] = hi; eidx[r] = i0 + 1; }
+          }
+        }
+      }
+      #pragma unroll
+      for (int r = 0; r < G; ++r) {
+        if (MATRIX) {
+          eb[g + r] = fminf(eb[g + r], e[r]);
+        } else if (e[r] < eb[g + r]) {            // tiles ascend: the lowest index keeps ties
+          eb[g + r] = e[r];
+          ei[g + r] = eidx[r];
+        }
+      }
+    }
+
+    // ---- end of a (direction, row block): emit ----
+    if (t == nt - 1) {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = rb * RB + r * TPB + tid;
+        if (row < rowcount) {
+          if (MATRIX) {
+            dsum += (double)eb[r];
+          } else {
+            float* dist = dir == 0 ? p.dist1 : p.dist2;
+            int* idx = dir == 0 ? p.idx1 : p.idx2;
+            const long long o = (long long)ci * rowcount + row;
+            dist[o] = eb[r];
+            if (idx) idx[o] = ei[r] == 0x7fffffff ? 0 : ei[r];
+          }
+        }
+      }
+    }
+    if (MATRIX && pos == seg0 - 1) { S0 = block_sum(dsum, red); dsum = 0.0; }
+    __syncthreads();   // everyone is done with tiles[buf] before it is refilled
+  }
+
+  if (MATRIX) {
+    const double S1 = block_sum(dsum, red);
+    if (tid == 0) {
+      const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
+      p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
+      if (p.symmetric && p.mirror && ci != cj) p.M[(long long)cj * p.ldm + ci] = v;
+    }
+  }
+}
+
+// xyz (clouds, count, 3) -> scan format (clouds, padded/2, 2) float4; padding is NaN so that it
+// never wins a min (FMNMX returns the non-NaN operand).
+__global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ xyz, long long clouds, int count,
+                                                   int padded, float4* __restrict__ out) {
+  const long long half = padded / 2;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= clouds * half) return;
+  const long long c = g / half;
+  const int q = (int)(g - c * half);
+  const float nan = __int_as_float(0x7fc00000);
+  float v[2][4];
+  #pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int pt = 2 * q + s;
+    if (pt < count) {
+      const float* src = xyz + (c * count + pt) * 3;
+      const float x = src[0], y = src[1], z = src[2];
+      v[s][0] = x; v[s][1] = y; v[s][2] = z;
+      v[s][3] = fmaf(z, z, fmaf(x, x, y * y));
+    } else {
+      v[s][0] = v[s][1] = v[s][2] = v[s][3] = nan;
+    }
+  }
+  out[g * 2] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+  out[g * 2 + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+}
+
+// Reference ChamferDistanceGradKernel (chamfer_distance.cu:148-172): own-term stores plus
+// scatter-adds through the arg-min indices.
+__global__ void __launch_bounds__(256) grad_kernel(int b, int n, const float* __restrict__ xyz1, int m,
+                                                   const float* __restrict__ xyz2, const float* __restrict__ gd1,
+                                                   const int* __restrict__ idx1, float* __restrict__ g1,
+                                                   float* __restrict__ g2) {
+  const long long total = (long long)b * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n;
+    const int j2 = idx1[e];
+    const float* a = xyz1 + e * 3;
+    const float* c = xyz2 + (i * m + j2) * 3;
+    const float g = gd1[e] * 2.0f;
+    const float gx = g * (a[0] - c[0]), gy = g * (a[1] - c[1]), gz = g * (a[2] - c[2]);
+    atomicAdd(g1 + e * 3 + 0, gx);
+    atomicAdd(g1 + e * 3 + 1, gy);
+    atomicAdd(g1 + e * 3 + 2, gz);
+    float* o = g2 + (i * m + j2) * 3;
+    atomicAdd(o + 0, -gx);
+    atomicAdd(o + 1, -gy);
+    atomicAdd(o + 2, -gz);
+  }
+}
+
+static int padded_of(int count) { return (count + CHUNK - 1) / CHUNK * CHUNK; }
+static size_t scan_bytes(long long clouds, int count) { return (size_t)clouds * padded_of(count) * 16; }
+
+static int pick_r(int maxcount) {
+  if (maxcount > TPB * 4) return 8;
+  if (maxcount > TPB * 2) return 4;
+  if (maxcount > TPB) return 2;
+  return 1;
+}
+
+template <int R, bool MATRIX>
+static int launch_nn(const Params& p, dim3 grid, cudaStream_t st) {
+  static bool configured = false;   // per (R, MATRIX) instantiation
+  if (!configured) {
+    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  nn_kernel<R, MATRIX><<<grid, TPB, SMEM_BYTES, st>>>(p);
+  DUSTY_AFTER_LAUNCH("chamfer nn_kernel");
+  return 0;
+}
+
+template <bool MATRIX>
+static int dispatch_nn(int r, const Params& p, dim3 grid, cudaStream_t st) {
+  switch (r) {
+    case 8: return launch_nn<8, MATRIX>(p, grid, st);
+    case 4: return launch_nn<4, MATRIX>(p, grid, st);
+    case 2: return launch_nn<2, MATRIX>(p, grid, st);
+    default: return launch_nn<1, MATRIX>(p, grid, st);
+  }
+}
+
+static int run_prep(const float* xyz, long long clouds, int count, float4* out, cudaStream_t st) {
+  const int padded = padded_of(count);
+  const long long work = clouds * (padded / 2);
+  if (work == 0) return 0;
+  prep_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(xyz, clouds, count, padded, out);
+  DUSTY_AFTER_LAUNCH("chamfer prep_kernel");
+  return 0;
+}
+
+}  // namespace chamfer
+}  // namespace dusty
+
+using namespace dusty;
+using namespace dusty::chamfer;
+
+extern "C" size_t dusty_chamfer_forward_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 0;
+  return align_up(scan_bytes(b, n), 256) + align_up(scan_bytes(b, m), 256);
+}
+
+extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b, int n, int m, float* dist1,
+                                     float* dist2, int32_t* idx1, int32_t* idx2, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (b < 0 || n < 0 || m < 0) return fail_arg(DUSTY_EINVAL, "chamfer_forward: negative size b=%d n=%d m=%d", b, n, m);
+  if (b == 0) return 0;
+  if (int rc = check_device()) return rc;
+  if (n == 0 || m == 0) {   // the reference leaves its pre-zeroed outputs untouched
+    if (n) { DUSTY_CUDA(cudaMemsetAsync(dist1, 0, sizeof(float) * b * n, st)); if (idx1) DUSTY_CUDA(cudaMemsetAsync(idx1, 0, sizeof(int) * b * n, st)); }
+    if (m) { DUSTY_CUDA(cudaMemsetAsync(dist2, 0, sizeof(float) * b * m, st)); if (idx2) DUSTY_CUDA(cudaMemsetAsync(idx2, 0, sizeof(int) * b * m, st)); }
+    return 0;
+  }
+  if (!xyz1 || !xyz2 || !dist1 || !dist2 || !workspace) return fail_arg(DUSTY_EINVAL, "chamfer_forward: null pointer");
+  if (b > 65535) return fail_arg(DUSTY_EINVAL, "chamfer_forward: batch %d exceeds 65535", b);
+  if (!aligned16(workspace)) return fail_arg(DUSTY_EALIGN, "chamfer_forward: workspace must be 16-byte aligned");
+  if (workspace_bytes < dusty_chamfer_forward_workspace_bytes(b, n, m))
+    return fail_arg(DUSTY_ENOSPACE, "chamfer_forward: workspace %zu < %zu", workspace_bytes,
+                    dusty_chamfer_forward_workspace_bytes(b, n, m));
+  float4* s1 = static_cast<float4*>(workspace);
+  float4* s2 = reinterpret_cast<float4*>(static_cast<char*>(workspace) + align_up(scan_bytes(b, n), 256));
+  if (int rc = run_prep(xyz1, b, n, s1, st)) return rc;
+  if (int rc = run_prep(xyz2, b, m, s2, st)) return rc;
+  Params p{};
+  p.scanX = s1; p.scanY = s2;
+  p.countX = n; p.countY = m;
+  p.paddedX = padded_of(n); p.paddedY = padded_of(m);
+  p.strideX = p.paddedX; p.strideY = p.paddedY;
+  p.dist1 = dist1; p.dist2 = dist2; p.idx1 = idx1; p.idx2 = idx2;
+  const int r = pick_r(n > m ? n : m);
+  const int rbmax = ((n > m ? n : m) + TPB * r - 1) / (TPB * r);
+  return dispatch_nn<false>(r, p, dim3(rbmax, b, 2), st);
+}
+
+extern "C" size_t dusty_chamfer_backward_workspace_bytes(int, int, int) { return 0; }
+
+extern "C" int dusty_chamfer_backward(const float* xyz1, const float* xyz2, int b, int n, int m,
+                                      const float* grad_dist1, const float* grad_dist2, const int32_t* idx1,
+                                      const int32_t* idx2, float* grad_xyz1, float* grad_xyz2, void*, size_t,
+                                      void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (b < 0 || n < 0 || m < 0) return fail_arg(DUSTY_EINVAL, "chamfer_backward: negative size");
+  if (b == 0) return 0;
+  if (int rc = check_device()) return rc;
+  if (n) DUSTY_CUDA(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * b * n, st));
+  if (m) DUSTY_CUDA(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * b * m, st));
+  if (n == 0 || m == 0) return 0;
+  if (!xyz1 || !xyz2 || !grad_dist1 || !grad_dist2 || !idx1 || !idx2 || !grad_xyz1 || !grad_xyz2)
+    return fail_arg(DUSTY_EINVAL, "chamfer_backward: null pointer");
+  const int g1 = (int)std::min<long long>(((long long)b * n + 255) / 256, 148LL * 16);
+  grad_kernel<<<g1, 256, 0, st>>>(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_xyz1, grad_xyz2);
+  DUSTY_AFTER_LAUNCH("chamfer grad_kernel");
+  const int g2 = (int)std::min<long long>(((long long)b * m + 255) / 256, 148LL * 16);
+  grad_kernel<<<g2, 256, 0, st>>>(b, m, xyz2, n, xyz1, grad_dist2, idx2, grad_xyz2, grad_xyz1);
+  DUSTY_AFTER_LAUNCH("chamfer grad_kernel");
+  return 0;
+}
+
+extern "C" size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, int pb) {
+  size_t s = 0;
+  if (na > 0 && pa > 0) s += align_up(scan_bytes(na, pa), 256);
+  if (nb > 0 && pb > 0) s += align_up(scan_bytes(nb, pb), 256);
+  return s;
+}
+
+extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float* B, int nb, int pb, int row_begin,
+                                    int row_end, int row_stride, int flags, float* M, long long ldm, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int symmetric = (flags & DUSTY_MATRIX_SYMMETRIC) != 0, mirror = (flags & DUSTY_MATRIX_MIRROR) != 0;
+  const int compact_rows = (flags & DUSTY_MATRIX_COMPACT_ROWS) != 0, prepared = (flags & DUSTY_MATRIX_PREPARED) != 0;
+  if (mirror && (!symmetric || compact_rows)) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: MIRROR needs SYMMETRIC and excludes COMPACT_ROWS");
+  if (na < 0 || nb < 0 || pa <= 0 || pb <= 0) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: bad sizes na=%d pa=%d nb=%d pb=%d", na, pa, nb, pb);
+  if (symmetric && (nb != na || pb != pa)) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: symmetric needs nb==na and pb==pa");
+  if (row_stride <= 0 || row_begin < 0 || row_end > na || ldm < nb)
+    return fail_arg(DUSTY_EINVAL, "chamfer_matrix: bad row range [%d,%d) stride %d of %d, ldm %lld", row_begin, row_end, row_stride, na, ldm);
+  if (row_begin >= row_end || nb == 0) return 0;
+  if (int rc = check_device()) return rc;
+  if (!A || !B || !M || !workspace) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: null pointer");
+  if (!aligned16(workspace)) return fail_arg(DUSTY_EALIGN, "chamfer_matrix: workspace must be 16-byte aligned");
+  const size_t need = dusty_chamfer_matrix_workspace_bytes(na, pa, symmetric ? 0 : nb, pb);
+  if (workspace_bytes < need) return fail_arg(DUSTY_ENOSPACE, "chamfer_matrix: workspace %zu < %zu", workspace_bytes, need);
+  float4* sa = static_cast<float4*>(workspace);
+  float4* sb = symmetric ? sa : reinterpret_cast<float4*>(static_cast<char*>(workspace) + align_up(scan_bytes(na, pa), 256));
+  if (!prepared) {
+    if (int rc = run_prep(A, na, pa, sa, st)) return rc;
+    if (!symmetric) if (int rc = run_prep(B, nb, pb, sb, st)) return rc;
+  }
+  const int rows = (row_end - row_begin + row_stride - 1) / row_stride;
+  if (rows > 65535) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: %d rows in one call exceeds 65535", rows);
+  Params p{};
+  p.scanX = sa; p.scanY = sb;
+  p.countX = pa; p.countY = pb;
+  p.paddedX = padded_of(pa); p.paddedY = padded_of(pb);
+  p.strideX = p.paddedX; p.strideY = p.paddedY;
+  p.row_begin = row_begin; p.row_stride = row_stride;
+  p.symmetric = symmetric; p.mirror = mirror; p.compact_rows = compact_rows;
+  p.M = M; p.ldm = ldm;
+  return dispatch_nn<true>(pick_r(pa > pb ? pa : pb), p, dim3(nb, rows, 1), st);
+}

@@ -1,0 +1,107 @@
+// Shared host/device helpers for libdustyb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "dusty_b200.h"
+
+namespace dusty {
+
+// ---- host side: error reporting and launch accounting (api.cu) ----
+int fail_cuda(cudaError_t e, const char* what);
+int fail_arg(int code, const char* fmt, ...);
+void count_launches(int n);
+int check_device();   // DUSTY_EARCH unless the current device is sm_10x
+
+constexpr int kNumSMs = 148;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define DUSTY_CUDA(call)                                                    \
+  do {                                                                      \
+    cudaError_t e__ = (call);                                               \
+    if (e__ != cudaSuccess) return ::dusty::fail_cuda(e__, #call);          \
+  } while (0)
+
+#define DUSTY_AFTER_LAUNCH(name)                                            \
+  do {                                                                      \
+    ::dusty::count_launches(1);                                             \
+    cudaError_t e__ = cudaGetLastError();                                   \
+    if (e__ != cudaSuccess) return ::dusty::fail_cuda(e__, name);           \
+  } while (0)
+
+// ---- device side: packed FP32 (FFMA2 / FADD2 / FMUL2), 3-input min, mbarrier + bulk copy ----
+#ifdef __CUDACC__
+
+typedef unsigned long long f32x2;   // two floats in one 64-bit register pair
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// streaming 128-bit global accesses that do not allocate in L1
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dusty

@@ -1,0 +1,165 @@
+"""MMD / COV / 1-NNA over Chamfer distance on libdustyb200 (mirror of reference
+utils/metrics/cov_mmd_1nna.py:19-139).
+
+The reference fills each matrix with a Python double loop (one row, 512 columns per iteration,
+>= 9 kernel launches each). Here one launch computes a whole matrix -- or, when the two sets have
+the same number of points per cloud, ONE launch computes the upper triangle of the stacked
+(N_ref+N_gen)^2 matrix that holds M_rr, M_rg and M_gg at once. When ``torch.distributed`` is
+initialised with more than one rank the rows of that matrix are sharded over the ranks and
+combined by a single all-gather (see ``sharding.py``).
+"""
+import numpy as np
+import torch
+
+from ... import _lib, sharding
+from .distance import chamfer_distance
+
+
+def compute_cd(pcs_1, pcs_2):
+    dl, dr = chamfer_distance(pcs_1, pcs_2)
+    return dl.mean(dim=1) + dr.mean(dim=1)
+
+
+def _check_clouds(pcs, name):
+    _lib.require_cuda(pcs, name)
+    if pcs.dim() != 3 or pcs.size(2) != 3:
+        raise ValueError(f"{name}: expected (B,P,3), got {tuple(pcs.shape)}")
+    return pcs.contiguous()
+
+
+def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None):
+    """M[i,j] = compute_cd(pcs_1[i], pcs_2[j]) in one launch. ``pcs_2=None`` declares the symmetric
+    case (upper triangle computed, mirrored unless ``compact_rows``). ``rows=(begin,end,stride)``
+    restricts the computation to a row shard."""
+    a = _check_clouds(pcs_1, "pcs_1")
+    symmetric = pcs_2 is None
+    b = a if symmetric else _check_clouds(pcs_2, "pcs_2")
+    na, pa, _ = a.shape
+    nb, pb, _ = b.shape
+    begin, end, stride = rows if rows is not None else (0, na, 1)
+    nrows = len(range(begin, end, stride))
+    flags = 0
+    if symmetric:
+        flags |= _lib.MATRIX_SYMMETRIC
+        if not compact_rows:
+            flags |= _lib.MATRIX_MIRROR
+    if compact_rows:
+        flags |= _lib.MATRIX_COMPACT_ROWS
+    if out is None:
+        out = torch.zeros(nrows if compact_rows else na, nb, device=a.device, dtype=torch.float32)
+    if na == 0 or nb == 0 or nrows == 0:
+        return out
+    if pa == 0 or pb == 0:
+        raise ValueError("clouds must hold at least one point")
+    lib = _lib.load()
+    nbytes = lib.dusty_chamfer_matrix_workspace_bytes(na, pa, 0 if symmetric else nb, pb)
+    ws = _lib.workspace(nbytes, a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dusty_chamfer_matrix(_lib.ptr(a), na, pa, _lib.ptr(b), nb, pb, begin, end, stride, flags,
+                                            _lib.ptr(out), out.stride(0), _lib.ptr(ws), nbytes, _lib.stream_of(a)),
+                   "dusty_chamfer_matrix")
+    return out
+
+
+def _pairwise_distance(pcs_1, pcs_2, batch_size, metrics=("cd",), verbose=True):
+    """{"cd": (B_1,B_2)} like the reference (cov_mmd_1nna.py:24-51). ``batch_size`` (the reference's
+    column block) and ``verbose`` (its tqdm bar) are accepted and have no effect."""
+    if "emd" in metrics:
+        raise NotImplementedError("EMD is not part of the path (the reference's extension does not build on "
+                                  "torch>=2 and its callers pass metrics=('cd',))")
+    distance = {}
+    if "cd" in metrics:
+        same = pcs_1 is pcs_2 or (pcs_1.data_ptr() == pcs_2.data_ptr() and pcs_1.shape == pcs_2.shape
+                                  and pcs_1.stride() == pcs_2.stride())
+        distance["cd"] = chamfer_matrix(pcs_1, None if same else pcs_2)
+    return distance
+
+
+def _compute_cov_mmd(M_rg):
+    N_ref, N_gen = M_rg.shape
+    mmd_gen, min_idx_gen = M_rg.min(dim=0)
+    mmd_ref, _ = M_rg.min(dim=1)
+    mmd = mmd_ref.mean().item()
+    mmd_gen = mmd_gen.mean().item()
+    cov = float(len(torch.unique(min_idx_gen))) / float(N_ref)
+    return {"mmd": mmd, "mmd-sample": mmd_gen, "cov": cov}
+
+
+def _nna_scores(tp, fp, fn, tn, total):
+    s = {"tp": tp, "fp": fp, "fn": fn, "tn": tn}
+    s.update({
+        "precision": s["tp"] / (s["tp"] + s["fp"] + 1e-10),
+        "recall": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
+        "accuracy_t": s["tp"] / (s["tp"] + s["fn"] + 1e-10),
+        "accuracy_f": s["tn"] / (s["tn"] + s["fp"] + 1e-10),
+        # torch.eq(label, pred).float().mean().item(): an f32 mean of 0/1 values
+        "accuracy": float(np.float32(tp + tn) / np.float32(total)),
+    })
+    return s
+
+
+def _finalize_device(M_rr, M_rg, M_gg):
+    """COV/MMD/1-NNA (k=1) in three small kernels, one 28-byte read-back."""
+    N_ref, N_gen = M_rg.shape
+    M_rr, M_rg, M_gg = M_rr.contiguous(), M_rg.contiguous(), M_gg.contiguous()
+    lib = _lib.load()
+    nbytes = lib.dusty_cov_mmd_1nna_workspace_bytes(N_ref, N_gen)
+    ws = _lib.workspace(nbytes, M_rg.device)
+    out = torch.empty(7, device=M_rg.device, dtype=torch.float32)
+    with torch.cuda.device(M_rg.device):
+        _lib.check(lib.dusty_cov_mmd_1nna_finalize(_lib.ptr(M_rr), _lib.ptr(M_rg), _lib.ptr(M_gg), N_ref, N_gen,
+                                                   _lib.ptr(out), _lib.ptr(ws), nbytes, _lib.stream_of(M_rg)),
+                   "dusty_cov_mmd_1nna_finalize")
+    o = [float(v) for v in out.tolist()]
+    cov_mmd = {"mmd": o[0], "mmd-sample": o[1], "cov": float(o[2]) / float(N_ref)}
+    return cov_mmd, _nna_scores(o[3], o[4], o[5], o[6], N_ref + N_gen)
+
+
+def _compute_nna(M_rr, M_rg, M_gg, k, sqrt=False):
+    """Leave-one-out k-NN two-sample test (reference cov_mmd_1nna.py:68-106). k=1 without sqrt -- the
+    only configuration any caller uses -- runs on the device kernels."""
+    if k == 1 and not sqrt:
+        return _finalize_device(M_rr, M_rg, M_gg)[1]
+    N_ref, N_gen = M_rg.shape
+    device = M_rg.device
+    label = torch.cat([torch.ones(N_ref, device=device), torch.zeros(N_gen, device=device)], dim=0)
+    M = torch.cat([torch.cat((M_rr, M_rg), dim=1), torch.cat((M_rg.t(), M_gg), dim=1)], dim=0)
+    M = M.abs().sqrt() if sqrt else M
+    M = M + torch.diag(float("inf") * torch.ones_like(label))
+    _, idx = M.topk(k=k, dim=0, largest=False)
+    count = torch.zeros_like(label)
+    for i in range(0, k):
+        count = count + label.index_select(0, idx[i])
+    pred = (count / k >= 0.5).float()
+    return _nna_scores((pred * label).sum().item(), (pred * (1 - label)).sum().item(),
+                       ((1 - pred) * label).sum().item(), ((1 - pred) * (1 - label)).sum().item(), N_ref + N_gen)
+
+
+def pairwise_matrices(pcs_gen, pcs_ref):
+    """(M_rr, M_rg, M_gg). Same point count: one stacked symmetric launch (row-sharded over the
+    process group when there is one); otherwise three launches."""
+    gen = _check_clouds(pcs_gen, "pcs_gen")
+    ref = _check_clouds(pcs_ref, "pcs_ref")
+    nr, ng = ref.size(0), gen.size(0)
+    if ref.size(1) == gen.size(1):
+        stacked = torch.cat([ref, gen], dim=0)
+        M = sharding.symmetric_chamfer_matrix(stacked)
+        return M[:nr, :nr], M[:nr, nr:], M[nr:, nr:]
+    return chamfer_matrix(ref), chamfer_matrix(ref, gen), chamfer_matrix(gen)
+
+
+@torch.no_grad()
+def compute_cov_mmd_1nna(pcs_gen, pcs_ref, batch_size, metrics=("cd",), verbose=True):
+    assert isinstance(metrics, tuple)
+    if "emd" in metrics:
+        raise NotImplementedError("EMD is not part of the path; pass metrics=('cd',)")
+    results = {}
+    if "cd" not in metrics:
+        return results
+    M_rr, M_rg, M_gg = pairwise_matrices(pcs_gen, pcs_ref)
+    cov_mmd, nna = _finalize_device(M_rr, M_rg, M_gg)
+    for k, v in cov_mmd.items():
+        results.update({"{}-{}".format(k, "cd"): v})
+    for k, v in nna.items():
+        results.update({"1-nn-{}-{}".format(k, "cd"): v})
+    return results

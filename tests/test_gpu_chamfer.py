@@ -1,0 +1,199 @@
+"""Chamfer kernels (through the Python mirror -> C ABI) against the oracle, the golden vectors and,
+when oracle/_ref is present, the reference's own CUDA kernel on the same GPU."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import lidar_like_clouds, rel_err, sampled_clouds
+from oracle import native, refload
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5      # north_star: Chamfer within 1e-5 relative (FP32)
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_forward(xyz1, xyz2):
+    from dusty_gan_b200.utils.metrics.distance.cd.chamfer_distance import ChamferDistanceFunction
+    from dusty_gan_b200 import _lib
+    a, b = cuda(xyz1), cuda(xyz2)
+    B, n, _ = a.shape
+    m = b.shape[1]
+    d1 = torch.empty(B, n, device="cuda"); d2 = torch.empty(B, m, device="cuda")
+    i1 = torch.empty(B, n, dtype=torch.int32, device="cuda"); i2 = torch.empty(B, m, dtype=torch.int32, device="cuda")
+    lib = _lib.load()
+    nbytes = lib.dusty_chamfer_forward_workspace_bytes(B, n, m)
+    ws = _lib.workspace(nbytes, a.device)
+    _lib.check(lib.dusty_chamfer_forward(_lib.ptr(a), _lib.ptr(b), B, n, m, _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(i1),
+                                         _lib.ptr(i2), _lib.ptr(ws), nbytes, _lib.stream_of(a)), "fwd")
+    torch.cuda.synchronize()
+    return d1.cpu().numpy(), d2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy()
+
+
+def check_against_oracle(xyz1, xyz2, exact_fraction=0.999):
+    d1, d2, i1, i2 = run_forward(xyz1, xyz2)
+    o1, o2, j1, j2 = native.chamfer_forward(xyz1, xyz2, rounding="cuda")
+    for d, o, i, j, other in ((d1, o1, i1, j1, xyz2), (d2, o2, i2, j2, xyz1)):
+        assert np.all(d >= o), "a reported distance can never be below the true minimum"
+        assert rel_err(d, o)[o > 0].max(initial=0.0) <= REL_TOL
+        assert np.all(d[o == 0] <= 1e-12)
+        same = d == o
+        assert same.mean() >= exact_fraction
+        assert np.all(i >= 0) and np.all(i < other.shape[1])
+        # wherever the value is the reference's minimum the index is the reference's (lowest on ties)
+        assert np.array_equal(i[same], j[same])
+    return d1, d2, i1, i2
+
+
+def test_forward_matches_golden_inputs(golden):
+    g = golden("chamfer_cpu.npz")
+    d1, d2, i1, i2 = check_against_oracle(g["xyz1"], g["xyz2"])
+    # the reference's CPU twin (unfused squares) agrees to rounding
+    assert np.allclose(d1, g["dist1"], rtol=2e-6, atol=1e-12) and np.allclose(d2, g["dist2"], rtol=2e-6, atol=1e-12)
+    assert i1[2, 0] == 149 and d1[2, 0] == 0.0           # exact hit
+    assert i2[0, 3] == g["idx2"][0, 3]
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 40), (31, 33), (32, 64), (255, 257), (2047, 2049), (2048, 2048),
+                                 (5000, 700), (700, 5000), (4097, 4100)])
+def test_forward_sizes(n, m):
+    rng = np.random.default_rng(n * 7919 + m)
+    check_against_oracle(rng.standard_normal((2, n, 3)).astype(np.float32) * 0.3,
+                         rng.standard_normal((2, m, 3)).astype(np.float32) * 0.3)
+
+
+def test_forward_lidar_clouds_with_dropped_pixels():
+    # un-sampled clouds keep dropped pixels as (0,0,0) points on both sides
+    a = lidar_like_clouds(3, 4096, 21)
+    b = lidar_like_clouds(3, 4096, 22)
+    d1, d2, i1, i2 = check_against_oracle(a, b)
+    zero_a = np.all(a == 0, -1)
+    first_zero_b = [int(np.argmax(np.all(b[k] == 0, -1))) for k in range(3)]
+    for k in range(3):
+        assert np.all(d1[k][zero_a[k]] == 0) and np.all(i1[k][zero_a[k]] == first_zero_b[k])
+
+
+def test_forward_empty_sides():
+    a = np.zeros((2, 0, 3), np.float32)
+    b = np.random.default_rng(0).standard_normal((2, 17, 3)).astype(np.float32)
+    d1, d2, i1, i2 = run_forward(a, b)
+    assert d1.shape == (2, 0) and np.all(d2 == 0) and np.all(i2 == 0)      # outputs left zero like the reference
+
+
+def test_forward_against_reference_cuda_kernel():
+    cd = refload.load("dustyref_cd")
+    if cd is None:
+        pytest.skip("oracle/_ref/dustyref_cd not built")
+    a = sampled_clouds(4, 2048, 31); b = sampled_clouds(4, 2048, 32)
+    ta, tb = cuda(a), cuda(b)
+    r1 = torch.zeros(4, 2048, device="cuda"); r2 = torch.zeros(4, 2048, device="cuda")
+    k1 = torch.zeros(4, 2048, dtype=torch.int32, device="cuda"); k2 = torch.zeros(4, 2048, dtype=torch.int32, device="cuda")
+    cd.forward_cuda(ta, tb, r1, r2, k1, k2)
+    torch.cuda.synchronize()
+    d1, d2, i1, i2 = run_forward(a, b)
+    for d, r, i, k in ((d1, r1, i1, k1), (d2, r2, i2, k2)):
+        r = r.cpu().numpy(); k = k.cpu().numpy()
+        assert np.all(d >= r) and rel_err(d, r).max() <= REL_TOL
+        assert (d == r).mean() >= 0.999 and np.array_equal(i[d == r], k[d == r])
+    # and the oracle's CUDA-rounding restatement IS the reference kernel, bit for bit
+    o1, o2, j1, j2 = native.chamfer_forward(a, b, rounding="cuda")
+    assert np.array_equal(o1, r1.cpu().numpy()) and np.array_equal(j1, k1.cpu().numpy())
+    assert np.array_equal(o2, r2.cpu().numpy()) and np.array_equal(j2, k2.cpu().numpy())
+
+
+def test_autograd_wrapper_and_backward(golden):
+    from dusty_gan_b200.utils.metrics.distance import chamfer_distance
+    g = golden("chamfer_cpu.npz")
+    a = cuda(g["xyz1"]).requires_grad_(True); b = cuda(g["xyz2"]).requires_grad_(True)
+    d1, d2 = chamfer_distance(a, b)
+    ((d1 * cuda(g["w1"])).sum() + (d2 * cuda(g["w2"])).sum()).backward()
+    o1, o2, j1, j2 = native.chamfer_forward(g["xyz1"], g["xyz2"], rounding="cuda")
+    gx1, gx2 = native.chamfer_backward(g["xyz1"], g["xyz2"], g["w1"], g["w2"], j1, j2)
+    assert np.allclose(a.grad.cpu().numpy(), gx1, rtol=1e-5, atol=1e-7)
+    assert np.allclose(b.grad.cpu().numpy(), gx2, rtol=1e-5, atol=1e-7)
+    assert np.allclose(a.grad.cpu().numpy(), g["grad1"], rtol=1e-4, atol=1e-6)
+
+
+def test_rejects_cpu_tensors():
+    from dusty_gan_b200.utils.metrics.distance import chamfer_distance
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        chamfer_distance(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+
+
+# ------------------------------------------------------------------ pairwise matrix ----------------
+def matrix(a, b=None, **kw):
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix
+    M = chamfer_matrix(cuda(a), None if b is None else cuda(b), **kw)
+    torch.cuda.synchronize()
+    return M.cpu().numpy()
+
+
+@pytest.mark.parametrize("P", [128, 512, 600, 2048])
+def test_matrix_against_oracle(P):
+    a = sampled_clouds(7, P, 100 + P); b = sampled_clouds(5, P, 200 + P)
+    M = matrix(a, b)
+    O = native.pairwise_cd(a, b, rounding="cuda")
+    assert rel_err(M, O).max() <= REL_TOL
+    S = matrix(a)
+    assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0)
+    assert rel_err(S, native.pairwise_cd(a, None, rounding="cuda"))[~np.eye(7, dtype=bool)].max() <= REL_TOL
+
+
+def test_matrix_unequal_point_counts_and_multi_tile():
+    a = sampled_clouds(3, 5000, 301); b = sampled_clouds(4, 2500, 302)
+    M = matrix(a, b)
+    assert rel_err(M, native.pairwise_cd(a, b, rounding="cuda")).max() <= REL_TOL
+
+
+def test_matrix_golden_reference_driver(golden):
+    g = golden("metrics_cpu.npz")
+    assert rel_err(matrix(g["ref"], g["gen"]), g["M_rg"]).max() <= REL_TOL
+    Mrr = matrix(g["ref"])
+    assert rel_err(Mrr, g["M_rr"])[~np.eye(12, dtype=bool)].max() <= REL_TOL and np.all(np.diag(Mrr) == 0)
+    Md = matrix(g["ref"], g["gen_dup"])
+    assert Md[5, 3] == 0.0
+
+
+def test_matrix_row_shards_are_bit_identical():
+    a = sampled_clouds(23, 512, 401)
+    full = matrix(a)
+    G = 4
+    parts = []
+    for r in range(G):
+        cap = (23 + G - 1) // G
+        blk = torch.zeros(cap, 23, device="cuda")
+        from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix
+        chamfer_matrix(cuda(a), None, rows=(r, 23, G), compact_rows=True, out=blk)
+        parts.append(blk)
+    from dusty_gan_b200 import sharding
+    U = sharding.assemble_upper(torch.stack(parts), 23, G)
+    S = sharding.symmetrize_upper(U).cpu().numpy()
+    assert np.array_equal(S, full)
+    b = sampled_clouds(9, 512, 402)
+    rect = matrix(a, b)
+    sub = matrix(a, b, rows=(4, 17, 3))
+    rows = list(range(4, 17, 3))
+    assert np.array_equal(sub[rows], rect[rows]) and np.all(np.delete(sub, rows, 0) == 0)
+
+
+def test_matrix_full_size_properties():
+    """Config 3 shape (1000 vs 1000 clouds, 2048 points): the stacked symmetric matrix in one launch,
+    checked through size-independent properties plus spot checks against the oracle."""
+    ref = sampled_clouds(1000, 2048, 501); gen = sampled_clouds(1000, 2048, 502)
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import pairwise_matrices
+    Mrr, Mrg, Mgg = [m.cpu().numpy() for m in pairwise_matrices(cuda(gen), cuda(ref))]
+    assert Mrr.shape == Mrg.shape == Mgg.shape == (1000, 1000)
+    for S in (Mrr, Mgg):
+        assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0)
+        assert np.all(S[~np.eye(1000, dtype=bool)] > 0)
+    assert np.all(np.isfinite(Mrg)) and np.all(Mrg > 0)
+    rng = np.random.default_rng(9)
+    for _ in range(6):
+        i, j = rng.integers(0, 1000, 2)
+        o = native.pairwise_cd(ref[i:i + 1], gen[j:j + 1], rounding="cuda")[0, 0]
+        assert abs(Mrg[i, j] - o) <= REL_TOL * o
+        o = native.pairwise_cd(gen[i:i + 1], gen[j:j + 1], rounding="cuda")[0, 0]
+        assert abs(Mgg[i, j] - o) <= REL_TOL * max(o, 1e-30)

@@ -1,0 +1,92 @@
+"""FPS kernel: indices bit-exact against the oracle's thread-by-thread replay of the reference
+kernel and, when oracle/_ref is present, against the reference's own CUDA kernel on this GPU."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import lidar_like_clouds
+from oracle import native, refload
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def fps_gpu(x, m):
+    from dusty_gan_b200.utils.sampling.fps import furthest_point_sampling
+    idx = furthest_point_sampling(cuda(x), m)
+    torch.cuda.synchronize()
+    assert idx.dtype == torch.int32
+    return idx.cpu().numpy()
+
+
+def test_full_resolution_clouds_bit_exact():
+    x = lidar_like_clouds(3, 32768, 7)                  # 64x512 range images, ~60 % eligible
+    assert np.array_equal(fps_gpu(x, 2048), native.fps(x, 2048))
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 4), (2, 2), (3, 3), (31, 8), (33, 33), (511, 64), (512, 512), (513, 100),
+                                 (1000, 1000), (2048, 512), (5000, 300), (20000, 128)])
+def test_sizes_bit_exact(n, m):
+    x = lidar_like_clouds(2, n, 1000 + n, dropped=0.2, near=0.1)
+    assert np.array_equal(fps_gpu(x, m), native.fps(x, m))
+
+
+def test_all_points_eligible_dense_cloud():
+    x = lidar_like_clouds(2, 32768, 8, dropped=0.0, near=0.0)      # exceeds the smem staging capacity
+    assert np.array_equal(fps_gpu(x, 512), native.fps(x, 512))
+
+
+def test_more_points_than_register_capacity():
+    x = lidar_like_clouds(1, 40000, 9, dropped=0.1, near=0.05)
+    assert np.array_equal(fps_gpu(x, 96), native.fps(x, 96))
+
+
+def test_degenerate_inputs():
+    # literal random-init generator: every range inside the exclusion radius => index 0 repeated (trap T1)
+    x = (np.random.default_rng(3).standard_normal((2, 4096, 3)) * 0.005).astype(np.float32)
+    assert np.all(fps_gpu(x, 64) == 0)
+    # dropped seed pixel, coincident points, fewer distinct points than samples: the tie rule decides
+    n = 1500
+    x = np.zeros((1, n, 3), np.float32)
+    x[0, [5, 77, 517, 1101, 300, 1401]] = [0.3, 0.1, 0.05]
+    x[0, 300] = [0.5, -0.2, 0.01]
+    assert np.array_equal(fps_gpu(x, 9), native.fps(x, 9))
+    # exact ties between different positions (mirror-symmetric pairs at equal distance from the seed)
+    rng = np.random.default_rng(4)
+    half = rng.uniform(0.05, 0.5, (600, 3)).astype(np.float32)
+    x = np.concatenate([half, half * np.array([1, -1, 1], np.float32)])[None]
+    x[0, 0] = [0.2, 0.0, 0.1]
+    assert np.array_equal(fps_gpu(x, 200), native.fps(x, 200))
+
+
+def test_downsample_and_gather():
+    from dusty_gan_b200.utils.sampling.fps import downsample_point_clouds, gather_operation, furthest_point_sampling
+    x = lidar_like_clouds(2, 8192, 12)
+    t = cuda(x)
+    sub = downsample_point_clouds(t, 256)
+    ref_sub, ref_idx = native.downsample_point_clouds(x, 256)
+    assert sub.shape == (2, 256, 3) and np.array_equal(sub.cpu().numpy(), ref_sub)
+    idx = furthest_point_sampling(t, 256)
+    feats = t.transpose(1, 2).contiguous().requires_grad_(True)
+    g = gather_operation(feats, idx)
+    assert np.array_equal(g.detach().cpu().numpy(), native.gather_points(x.transpose(0, 2, 1), ref_idx))
+    w = torch.rand_like(g)
+    (g * w).sum().backward()
+    expect = torch.zeros_like(feats).scatter_add_(2, idx.long()[:, None, :].expand(-1, 3, -1), w)
+    assert torch.allclose(feats.grad, expect)
+
+
+def test_against_reference_cuda_kernel():
+    ref = refload.load("dustyref_fps")
+    if ref is None:
+        pytest.skip("oracle/_ref/dustyref_fps not built")
+    for n, m, seed in ((32768, 2048, 21), (5000, 512, 22), (700, 64, 23)):
+        x = lidar_like_clouds(3, n, seed)
+        t = cuda(x)
+        r = ref.furthest_point_sampling(t, m)
+        torch.cuda.synchronize()
+        assert np.array_equal(fps_gpu(x, m), r.cpu().numpy())
+        assert np.array_equal(native.fps(x, m), r.cpu().numpy())       # pins the oracle too

@@ -1,0 +1,106 @@
+"""MMD / COV / 1-NNA driver and the end-to-end generate-and-evaluate slice on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import head_inputs, sampled_clouds
+from oracle import head_projection as hp
+from oracle import metrics as om
+from oracle import native
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["mmd-cd", "mmd-sample-cd", "cov-cd"] + ["1-nn-%s-cd" % k for k in
+                                               ("tp", "fp", "fn", "tn", "precision", "recall", "accuracy_t", "accuracy_f", "accuracy")]
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_scores_match_reference_golden(golden):
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import compute_cov_mmd_1nna
+    g = golden("metrics_cpu.npz")
+    scores = compute_cov_mmd_1nna(cuda(g["gen"]), cuda(g["ref"]), 512, ("cd",), verbose=False)
+    ref = dict(zip([str(k) for k in g["score_keys"]], g["score_values"]))
+    assert sorted(scores) == sorted(ref) == sorted(KEYS)
+    for k, v in ref.items():
+        assert isinstance(scores[k], float)
+        assert scores[k] == pytest.approx(v, rel=1e-5, abs=1e-12), k
+
+
+def test_scores_match_oracle_on_unequal_sets():
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import compute_cov_mmd_1nna
+    ref = sampled_clouds(40, 512, 61); gen = sampled_clouds(33, 512, 62) * np.float32(1.05)
+    scores = compute_cov_mmd_1nna(cuda(gen), cuda(ref), 512, ("cd",), verbose=False)
+    expect = om.compute_cov_mmd_1nna(gen, ref)
+    for k in KEYS:
+        assert scores[k] == pytest.approx(expect[k], rel=1e-5, abs=1e-12), k
+    # unequal point counts take the three-launch path
+    gen2 = sampled_clouds(12, 300, 63)
+    s2 = compute_cov_mmd_1nna(cuda(gen2), cuda(ref[:15]), 512, ("cd",), verbose=False)
+    e2 = om.compute_cov_mmd_1nna(gen2, ref[:15])
+    for k in KEYS:
+        assert s2[k] == pytest.approx(e2[k], rel=1e-5, abs=1e-12), k
+
+
+def test_finalize_kernel_against_numpy():
+    from dusty_gan_b200.utils.metrics import cov_mmd_1nna as m
+    rng = np.random.default_rng(5)
+    nr, ng = 57, 41
+    A = rng.uniform(0.1, 1.0, (nr + ng, nr + ng)).astype(np.float32)
+    A = np.minimum(A, A.T)
+    np.fill_diagonal(A, 0)
+    Mrr, Mrg, Mgg = A[:nr, :nr], A[:nr, nr:], A[nr:, nr:]
+    cm, nna = m._finalize_device(cuda(Mrr), cuda(Mrg), cuda(Mgg))
+    e = om.scores_from_matrices(Mrr, Mrg, Mgg)
+    assert cm["mmd"] == pytest.approx(e["mmd-cd"], rel=1e-6) and cm["mmd-sample"] == pytest.approx(e["mmd-sample-cd"], rel=1e-6)
+    assert cm["cov"] == e["cov-cd"]
+    for k in ("tp", "fp", "fn", "tn", "accuracy"):
+        assert nna[k] == pytest.approx(e["1-nn-%s-cd" % k], rel=1e-7), k
+    # the torch-op mirrors of the reference helpers agree with the kernels
+    t = m._compute_cov_mmd(cuda(Mrg))
+    assert t["cov"] == cm["cov"] and t["mmd"] == pytest.approx(cm["mmd"], rel=1e-6)
+    assert m._compute_nna(cuda(Mrr), cuda(Mrg), cuda(Mgg), 1)["tp"] == nna["tp"]
+    assert m._compute_nna(cuda(Mrr), cuda(Mrg), cuda(Mgg), 3)["tp"] >= 0
+
+
+def test_pairwise_distance_signature():
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import _pairwise_distance, compute_cd
+    a = cuda(sampled_clouds(6, 256, 71)); b = cuda(sampled_clouds(4, 256, 72))
+    d = _pairwise_distance(a, b, 512, ("cd",), False)
+    assert set(d) == {"cd"} and d["cd"].shape == (6, 4)
+    row = compute_cd(a[[2]].expand(4, -1, -1), b)           # the reference's inner-loop call
+    assert torch.allclose(d["cd"][2], row, rtol=1e-6, atol=0)
+    s = _pairwise_distance(a, a, 512, ("cd",), False)["cd"]
+    assert torch.equal(s, s.t())
+    with pytest.raises(NotImplementedError):
+        _pairwise_distance(a, b, 512, ("cd", "emd"), False)
+
+
+def test_generate_and_evaluate_slice():
+    """Config 1 in miniature: head -> projection -> FPS -> matrices -> scores, GPU against the oracle
+    chain fed the same tensors stage by stage."""
+    from dusty_gan_b200.models.dusty import DUSty1
+    from dusty_gan_b200.utils.lidar import LiDAR, synthetic_hdl64e_angles
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import compute_cov_mmd_1nna
+    from dusty_gan_b200 import pipeline
+    H, W, P, N = 64, 512, 256, 6
+    lidar = LiDAR(H, W, 0.9, 120.0, angle=synthetic_hdl64e_angles()).cuda()
+    head = DUSty1(torch.nn.Identity(), tau=1.0).cuda().eval()
+    sets = {}
+    for name, seed in (("gen", 1), ("ref", 2)):
+        depth, conf, u1, u2 = head_inputs(N, 1, H, W, seed, "cuda")
+        if head.gumbel.fixed_noise is None:
+            head.gumbel.fixed_noise = head.gumbel._logistic_from_uniform(u1, u2)
+        pts, out = pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, P, tol=0.0)
+        _, dout = hp.maskout_dusty1(depth, conf, head.gumbel.fixed_noise)
+        dense = hp.project_2d_to_3d_dense(dout, lidar.angle, 0.9, 120.0, 0.0)
+        assert torch.equal(out["points"], dense)
+        sub, _ = native.downsample_point_clouds(dense.cpu().numpy(), P)
+        assert np.array_equal(pts.cpu().numpy(), sub)
+        sets[name] = pts
+    scores = compute_cov_mmd_1nna(sets["gen"], sets["ref"], 512, ("cd",), verbose=False)
+    expect = om.compute_cov_mmd_1nna(sets["gen"].cpu().numpy(), sets["ref"].cpu().numpy())
+    for k in KEYS:
+        assert scores[k] == pytest.approx(expect[k], rel=1e-5, abs=1e-12), k
