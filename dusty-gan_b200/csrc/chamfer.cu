@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
   };
   if (tid == 0) issue(pos_begin, 0);
 
-  float nax[R], nay[R], naz[R];     // -2 * row coordinates (search operands)
+  f32x2 nax[R], nay[R], naz[R];     // {-2a, -2a}: search operands; ptxas folds the pair into FFMA2's scalar-broadcast form
   float eb[R];                      // exact running minimum over tiles
   int ei[R];                        // its index (batch front end only)
   double dsum = 0.0, S0 = 0.0;
@@ -141,9 +141,10 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
         const int rr = row < rowcount ? row : 0;
         const float4 a0 = rows[(rr >> 1) * 2], a1 = rows[(rr >> 1) * 2 + 1];
         const bool hi = rr & 1;
-        nax[r] = -2.0f * (hi ? a0.y : a0.x);
-        nay[r] = -2.0f * (hi ? a0.w : a0.z);
-        naz[r] = -2.0f * (hi ? a1.y : a1.x);
+        const float mx = -2.0f * (hi ? a0.y : a0.x), my = -2.0f * (hi ? a0.w : a0.z), mz = -2.0f * (hi ? a1.y : a1.x);
+        nax[r] = pack2(mx, mx);
+        nay[r] = pack2(my, my);
+        naz[r] = pack2(mz, mz);
         eb[r] = __int_as_float(0x7f800000);
         ei[r] = 0;
       }
@@ -168,9 +169,9 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
         const f32x2 bz = pack2(q1.x, q1.y), bn = pack2(q1.z, q1.w);
         #pragma unroll
         for (int r = 0; r < R; ++r) {
-          f32x2 s = fma2(pack2(naz[r], naz[r]), bz, bn);
-          s = fma2(pack2(nay[r], nay[r]), by, s);
-          s = fma2(pack2(nax[r], nax[r]), bx, s);
+          f32x2 s = fma2(naz[r], bz, bn);
+          s = fma2(nay[r], by, s);
+          s = fma2(nax[r], bx, s);
           float lo, hi;
           unpack2(s, lo, hi);
           cm[r] = (k == 0) ? fminf(lo, hi) : min3(cm[r], lo, hi);
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
       for (int r = 0; r < G; ++r) {
         e[r] = __int_as_float(0x7f800000);
         eidx[r] = 0x7fffffff;
-        const float x = -0.5f * nax[g + r], y = -0.5f * nay[g + r], z = -0.5f * naz[g + r];
-        ax2[r] = pack2(x, x); ay2[r] = pack2(y, y); az2[r] = pack2(z, z);
+        const f32x2 mh = pack2(-0.5f, -0.5f);      // exact: recovers the row point from -2a
+        ax2[r] = mul2(nax[g + r], mh); ay2[r] = mul2(nay[g + r], mh); az2[r] = mul2(naz[g + r], mh);
         cp[r] = tp + cid[g + r] * CHUNK;
       }
       #pragma unroll 4

@@ -102,13 +102,25 @@ __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
   unsigned vbits[ITERS];
   int tcount = 0;
 
+  // all streaming loads of this thread first: 2-3 independent 128-bit requests per iteration in flight
+  float4 dvs[ITERS], cvs[ITERS], c1s[C == 2 ? ITERS : 1];
+  #pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int pix = seg * SEG + it * (TPB * 4) + tid * 4;
+    if (pix < npix) {
+      dvs[it] = ldg_stream(reinterpret_cast<const float4*>(depth + pix));
+      cvs[it] = ldg_stream(reinterpret_cast<const float4*>(conf0 + pix));
+      if (C == 2) c1s[it] = ldg_stream(reinterpret_cast<const float4*>(conf0 + npix + pix));
+    }
+  }
+
   #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int pix = seg * SEG + it * (TPB * 4) + tid * 4;
     vbits[it] = 0;
     if (pix < npix) {
-      const float4 dv = ldg_stream(reinterpret_cast<const float4*>(depth + pix));
-      const float4 cv = ldg_stream(reinterpret_cast<const float4*>(conf0 + pix));
+      const float4 dv = dvs[it];
+      const float4 cv = cvs[it];
       float4 na = make_float4(0, 0, 0, 0), nb = na;
       if (a.gp.mode != DUSTY_NOISE_NONE) na = load_noise(a.gp, a.gp.a, img, pix);
       if (a.gp.mode == DUSTY_NOISE_UNIFORM) nb = load_noise(a.gp, a.gp.b, img, pix);
@@ -117,7 +129,7 @@ __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
       float mk[4] = {mp[0], mp[1], mp[2], mp[3]};
       stg_stream(reinterpret_cast<float4*>(omask0 + pix), make_float4(mp[0], mp[1], mp[2], mp[3]));
       if (C == 2) {
-        const float4 c1 = ldg_stream(reinterpret_cast<const float4*>(conf0 + npix + pix));
+        const float4 c1 = c1s[C == 2 ? it : 0];
         float4 ia = make_float4(0, 0, 0, 0), ib = ia;
         if (a.gi.mode != DUSTY_NOISE_NONE) ia = load_noise(a.gi, a.gi.a, img, pix);
         if (a.gi.mode == DUSTY_NOISE_UNIFORM) ib = load_noise(a.gi, a.gi.b, img, pix);

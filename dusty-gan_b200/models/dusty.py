@@ -143,8 +143,22 @@ def _projection_fields(params, lidar, tol):
     params.inv_max_depth = f32(1.0) / f32(lidar.max_depth)
 
 
-def _head_call(module, output, threshold, lidar=None, tol=1e-8, points_layout=1, compact=False):
-    """Shared body of maskout (lidar=None) and the fused generate->points path (lidar given)."""
+def _drop_value(module):
+    """The drop_const buffer as a host float, read back once per buffer version (a per-call
+    ``float(tensor)`` would put a device synchronisation on the hot path)."""
+    key = (module.drop_const._version, module.drop_const.data_ptr())
+    cached = getattr(module, "_drop_cache", None)
+    if cached is None or cached[0] != key:
+        cached = (key, float(module.drop_const))
+        object.__setattr__(module, "_drop_cache", cached)
+    return cached[1]
+
+
+def _head_call(module, output, threshold, lidar=None, tol=1e-8, points_layout=1, compact=False, buffers=None):
+    """Shared body of maskout (lidar=None) and the fused generate->points path (lidar given).
+    ``buffers`` may hold preallocated ``mask``, ``depth``, ``points`` tensors to write into (steady-state
+    callers reuse them; the evaluate loop of the reference reallocates every batch)."""
+    buffers = buffers or {}
     assert isinstance(output, dict)
     assert "confidence" in output
     assert "depth" in output
@@ -178,15 +192,21 @@ def _head_call(module, output, threshold, lidar=None, tol=1e-8, points_layout=1,
     p.inv_tau = gm._inv_tau()
     p.threshold = np.float32(threshold)
     p.eps = np.float32(gm.eps)
-    p.drop_const = np.float32(float(module.drop_const))
+    p.drop_const = np.float32(_drop_value(module))
     p.points_layout = points_layout
-    mask = torch.empty_like(c)
-    dout = torch.empty_like(d)
+    mask = buffers["mask"] if "mask" in buffers else torch.empty_like(c)
+    dout = buffers["depth"] if "depth" in buffers else torch.empty_like(d)
+    for t, like in ((mask, c), (dout, d)):
+        if t.shape != like.shape or t.dtype != torch.float32 or t.device != d.device or not t.is_contiguous():
+            raise ValueError("preallocated buffer does not match the expected shape/dtype/device")
     points = count = index = compacted = trig = ws = None
     if lidar is not None:
         _projection_fields(p, lidar, tol)
         trig = lidar.trig_table(d.device)
-        points = torch.empty((B, H * W, 3) if points_layout == 1 else (B, 3, H, W), device=d.device, dtype=torch.float32)
+        pshape = (B, H * W, 3) if points_layout == 1 else (B, 3, H, W)
+        points = buffers["points"] if "points" in buffers else torch.empty(pshape, device=d.device, dtype=torch.float32)
+        if tuple(points.shape) != pshape or points.dtype != torch.float32 or not points.is_contiguous():
+            raise ValueError("preallocated points buffer does not match the expected shape/dtype")
         if compact:
             count = torch.empty(B, device=d.device, dtype=torch.int32)
             index = torch.empty(B, H * W, device=d.device, dtype=torch.int32)

@@ -12,13 +12,13 @@ from .utils.sampling.fps import downsample_point_clouds
 
 
 @torch.no_grad()
-def maskout_and_project(head, output, lidar, tol=0.0, threshold=0.5, compact=False):
+def maskout_and_project(head, output, lidar, tol=0.0, threshold=0.5, compact=False, buffers=None):
     """``head`` is a DUSty1/DUSty2 module, ``output`` the backbone's dict. Returns the dict updated like
     ``maskout`` plus ``points`` (B,H*W,3) -- the contiguous layout FPS consumes -- and, with
     ``compact=True``, ``valid_count`` (B,), ``valid_index`` (B,H*W) and ``valid_points`` (B,H*W,3):
     the valid pixels of each image in ascending pixel order (what ``points[i][valid[i]]`` selects)."""
     out, points, count, index, compacted = _head_call(head, output, threshold, lidar=lidar, tol=tol,
-                                                      points_layout=1, compact=compact)
+                                                      points_layout=1, compact=compact, buffers=buffers)
     out["points"] = points
     if compact:
         out["valid_count"], out["valid_index"], out["valid_points"] = count, index, compacted

@@ -15,6 +15,10 @@ from ... import _lib, sharding
 from .distance import chamfer_distance
 
 
+# When bench.py sets this to a list, every matrix launch appends a (start, end) CUDA event pair.
+KERNEL_EVENTS = None
+
+
 def compute_cd(pcs_1, pcs_2):
     dl, dr = chamfer_distance(pcs_1, pcs_2)
     return dl.mean(dim=1) + dr.mean(dim=1)
@@ -55,9 +59,15 @@ def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None):
     nbytes = lib.dusty_chamfer_matrix_workspace_bytes(na, pa, 0 if symmetric else nb, pb)
     ws = _lib.workspace(nbytes, a.device)
     with torch.cuda.device(a.device):
+        if KERNEL_EVENTS is not None:       # bench.py: device time of the launch on its own stream
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _lib.check(lib.dusty_chamfer_matrix(_lib.ptr(a), na, pa, _lib.ptr(b), nb, pb, begin, end, stride, flags,
                                             _lib.ptr(out), out.stride(0), _lib.ptr(ws), nbytes, _lib.stream_of(a)),
                    "dusty_chamfer_matrix")
+        if KERNEL_EVENTS is not None:
+            ev[1].record()
+            KERNEL_EVENTS.append(ev)
     return out
 
 

@@ -11,7 +11,7 @@ are the strongest parity oracle (reference CUDA code running on the same B200).
 Three artefacts:
   dustyref_cd      as shipped: ``load()`` is called with no flags in the reference
                    (cd/chamfer_distance.py:7-13) => g++ -O0 for the CPU twin.
-  dustyref_cd_o3   same sources, ``-O3 -march=native`` ("honest CPU" baseline of BASELINE.md §3.2).
+  dustyref_cd_o3   same sources, ``-O3`` (baseline ISA so the .so runs on any host; "honest CPU" arm of BASELINE.md section 3.2).
   dustyref_fps     the PointNet++ FPS/gather kernels (fps/furthest_point_sampling.py:10-16).
 
 Run:  python oracle/build_ref.py            (no-op when /root/reference is absent)
@@ -31,7 +31,7 @@ TARGETS = {
     "dustyref_cd_o3": dict(
         sources=["utils/metrics/distance/cd/chamfer_distance.cpp",
                  "utils/metrics/distance/cd/chamfer_distance.cu"],
-        extra_cflags=["-O3", "-march=x86-64-v3"]),
+        extra_cflags=["-O3"]),
     "dustyref_fps": dict(
         sources=["utils/sampling/fps/furthest_point_sampling.cpp",
                  "utils/sampling/fps/furthest_point_sampling.cu"],
