@@ -197,3 +197,14 @@ def test_matrix_full_size_properties():
         assert abs(Mrg[i, j] - o) <= REL_TOL * o
         o = native.pairwise_cd(gen[i:i + 1], gen[j:j + 1], rounding="cuda")[0, 0]
         assert abs(Mgg[i, j] - o) <= REL_TOL * max(o, 1e-30)
+
+
+def test_forward_against_reference_cuda_golden(golden):
+    g = golden("gpu_reference_kernels.npz")
+    for i in range(3):
+        b, n, m, seed = [int(v) for v in g[f"cd{i}_case"]]
+        a = sampled_clouds(b, n, seed); c = lidar_like_clouds(b, m, seed + 1)
+        d1, d2, i1, i2 = run_forward(a, c)
+        for d, r, ix, k in ((d1, g[f"cd{i}_dist1"], i1, g[f"cd{i}_idx1"]), (d2, g[f"cd{i}_dist2"], i2, g[f"cd{i}_idx2"])):
+            assert np.all(d >= r) and rel_err(d, r)[r > 0].max() <= REL_TOL
+            assert (d == r).mean() >= 0.999 and np.array_equal(ix[d == r], k[d == r])

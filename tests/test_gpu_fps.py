@@ -90,3 +90,15 @@ def test_against_reference_cuda_kernel():
         torch.cuda.synchronize()
         assert np.array_equal(fps_gpu(x, m), r.cpu().numpy())
         assert np.array_equal(native.fps(x, m), r.cpu().numpy())       # pins the oracle too
+
+
+def test_against_reference_cuda_golden(golden):
+    """The committed outputs of the reference's CUDA kernel (oracle/gen_golden_gpu.py on a B200)."""
+    g = golden("gpu_reference_kernels.npz")
+    i = 0
+    while f"fps{i}_case" in g:
+        b, n, m, seed, dropped, near = [int(v) for v in g[f"fps{i}_case"]]
+        x = lidar_like_clouds(b, n, seed, dropped=dropped / 1000, near=near / 1000)
+        assert np.array_equal(fps_gpu(x, m), g[f"fps{i}_idx"]), g[f"fps{i}_case"]
+        i += 1
+    assert np.array_equal(fps_gpu(g["fps_deg_input"], 200), g["fps_deg_idx"])

@@ -144,3 +144,28 @@ def test_fps_oracle_small_n_block_sizes():
         m = min(n, 9)
         idx = native.fps(x, m)
         assert idx.shape == (1, m) and idx.min() >= 0 and idx.max() < n
+
+
+# ---- oracle vs the reference's own CUDA kernels run on a B200 (oracle/gen_golden_gpu.py) ----
+def test_fps_oracle_matches_reference_cuda_kernel_outputs(golden):
+    g = golden("gpu_reference_kernels.npz")
+    i = 0
+    while f"fps{i}_case" in g:
+        b, n, m, seed, dropped, near = [int(v) for v in g[f"fps{i}_case"]]
+        if n * m * b <= 32768 * 512 * 2:                  # keep the CPU suite short; the rest runs in -m gpu
+            x = lidar_like_clouds(b, n, seed, dropped=dropped / 1000, near=near / 1000)
+            assert np.array_equal(native.fps(x, m), g[f"fps{i}_idx"]), g[f"fps{i}_case"]
+        i += 1
+    assert i >= 6
+    assert np.array_equal(native.fps(g["fps_deg_input"], 200), g["fps_deg_idx"])
+
+
+def test_chamfer_cuda_rounding_matches_reference_cuda_kernel_outputs(golden):
+    from helpers import sampled_clouds
+    g = golden("gpu_reference_kernels.npz")
+    for i in (1,):                                        # (2,1000,777): seconds on the CPU
+        b, n, m, seed = [int(v) for v in g[f"cd{i}_case"]]
+        a = sampled_clouds(b, n, seed); c = lidar_like_clouds(b, m, seed + 1)
+        d1, d2, i1, i2 = native.chamfer_forward(a, c, rounding="cuda")
+        assert np.array_equal(d1, g[f"cd{i}_dist1"]) and np.array_equal(d2, g[f"cd{i}_dist2"])
+        assert np.array_equal(i1, g[f"cd{i}_idx1"]) and np.array_equal(i2, g[f"cd{i}_idx2"])
