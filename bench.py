@@ -44,6 +44,15 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch from the committed ncu --set full capture of this round (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(key)
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -181,7 +190,8 @@ def bench_stages(device, hbm_gbs, peak_src, flush):
             "images_per_s": HEAD_BATCH / t, "ms": t * 1e3, "single_api_call_ms": api_ms,
             "roofline": {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                          "frac": bytes_alg / t / 1e9 / hbm_gbs, "peak_source": peak_src,
-                         "algorithmic_bytes": bytes_alg, "traffic": None},
+                         "algorithmic_bytes": bytes_alg,
+                         "traffic": ncu_traffic("head_project_dusty1_b256") if kind == 1 else None},
             "note": f"configs[1]: batch {HEAD_BATCH} of {H}x{W}; {reps} launches replayed as a CUDA graph, outputs preallocated; "
                     "working set per launch exceeds L2"}
     head = make_head(1, device)
@@ -407,7 +417,8 @@ def main():
         "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json holds no FP32 figure)",
         "peak_probe_ffma_only": peak_probe, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step,
         "algorithmic_flops_per_entry": flops_per_entry, "entries_per_launch_algorithmic": entries / world,
-        "entries_per_launch_executed": exe_entries / world, "traffic": None,
+        "entries_per_launch_executed": exe_entries / world,
+        "traffic": ncu_traffic("chamfer_nn_kernel_n1000") if (world == 1 and N == N_CLOUDS) else None,
         "note": "algorithmic = 3 N^2 entries x 12 P^2 flop (what the reference fills); executed = stacked upper triangle "
                 "(M_rr and M_gg are symmetric, SURVEY.md S8), same 12 P^2 flop per entry"}
 

@@ -13,15 +13,28 @@
 //   T = min(2^floor(log2 n), 512) is its block size and L = log2 T. With no eligible point every
 //   pick is index 0.
 //
-// How this kernel does it: one CTA per cloud.
-//   prologue  eligible points are compacted *in tie-break order* (so "lowest compact index" is the
-//             reference's tie rule) into a SoA copy whose first SMEM_CAP points live in shared
-//             memory (the remainder, if any, is read from the L2-resident workspace copy);
-//   loop      running distances never leave registers (up to 64 per thread); each iteration is one
-//             pass over the staged coordinates with packed FP32 math (sub/mul/fma.f32x2), a warp
-//             REDUX arg-max, one smem hop across the 16 warps and a single __syncthreads (result
-//             slots are double buffered by iteration parity);
-//   epilogue  compact indices -> original indices, and the gather of the sampled xyz.
+// Two kernels, one CTA per cloud each:
+//
+// fps_pruned_kernel (n <= 32768, the path every config takes)
+//   prologue  eligible points are counting-sorted by a 4096-cell grid (x,y Morton-interleaved, z low
+//             bits) into a SoA copy -- first SMEM_CAP points in shared memory, the rest in the
+//             L2-resident workspace -- so that the 128 points owned by one (warp, slot) pair form a
+//             spatially tight *bucket*; each bucket keeps its bounding box and (max distance, tie
+//             key, position, original index) of its current best point in shared memory;
+//   loop      running distances never leave registers (64 per thread). Per iteration a lane tests
+//             one bucket: LB = fma(gz,gz,fma(gx,gx,gy*gy)) on the per-axis gaps between the new
+//             centre and the box. Every operation of the reference's distance is monotone in
+//             |dx|,|dy|,|dz| and rounding is monotone, so LB <= d(k) for every point k of the bucket
+//             *in floating point*; when LB >= the bucket's max distance no fminf can change
+//             anything and the bucket is skipped -- results stay bit-identical while late
+//             iterations touch only the buckets near the new centre. Touched buckets are updated
+//             with packed FP32 math (sub/mul/fma.f32x2) and re-elect their best point with warp
+//             REDUX; the block arg-max is a REDUX over bucket records, one smem hop across the 16
+//             warps and a single __syncthreads (slots double buffered by iteration parity);
+//   ties      resolved explicitly on the reference's key (bitreverse_L(k mod T), k div T).
+//
+// fps_flat_kernel (n > 32768, or DUSTY_FPS_FLAT=1): no pruning; points compacted in tie-break
+//   order, distances in registers (or, beyond 32768 points, in the workspace).
 #include <algorithm>
 
 #include "common.cuh"

@@ -7,9 +7,9 @@ mkdir -p gpurun_out
 # 1. every launch of the default bench command with its device time (cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${R}.csv \
     python bench.py --steps 2 --warmup 1 --skip-extras > gpurun_out/bench_under_ncu_${R}.log 2>&1
-# 2. the dominant kernel, full set, on a reduced cloud count (same kernel, same per-CTA work)
+# 2. the dominant kernel, full set, at the bench's own size (2 s kernel, ~40 replays)
 ncu --set full --clock-control none --import-source on -k regex:nn_kernel -s 1 -c 1 -f -o gpurun_out/prof_chamfer_${R} \
-    python bench.py --clouds 200 --steps 1 --warmup 1 --skip-extras > gpurun_out/prof_chamfer_${R}.log 2>&1
+    python bench.py --steps 1 --warmup 1 --skip-extras > gpurun_out/prof_chamfer_${R}.log 2>&1
 # 3. head + projection and FPS kernels
 ncu --set full --clock-control none --import-source on -k regex:"head_project_kernel|fps_kernel" -s 2 -c 2 -f \
     -o gpurun_out/prof_stages_${R} python profiles/stage_driver.py > gpurun_out/prof_stages_${R}.log 2>&1
