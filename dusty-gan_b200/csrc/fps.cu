@@ -36,6 +36,7 @@
 // fps_flat_kernel (n > 32768, or DUSTY_FPS_FLAT=1): no pruning; points compacted in tie-break
 //   order, distances in registers (or, beyond 32768 points, in the workspace).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -69,9 +70,10 @@ __device__ __forceinline__ int block_exscan(int v, int* total, int* wsum) {
   return base + inc - v;
 }
 
-// comp layout per cloud (float, n_pad = n rounded up to 4): x[n_pad] y[n_pad] z[n_pad] oidx[n_pad]
+// comp layout per cloud (float, n_pad = n rounded up to 4, inside a block sized for n rounded up to 128):
+// x[n_pad] y[n_pad] z[n_pad] oidx[n_pad]
 template <bool FITS_REG>
-__global__ void __launch_bounds__(TPB, 1) fps_kernel(const float* __restrict__ xyz_all, int n, int m,
+__global__ void __launch_bounds__(TPB, 1) fps_flat_kernel(const float* __restrict__ xyz_all, int n, int m,
                                                      int* __restrict__ idx_all, float* __restrict__ out_all,
                                                      float* __restrict__ comp_all, float* __restrict__ temp_all) {
   extern __shared__ __align__(16) float sm[];
@@ -80,7 +82,6 @@ __global__ void __launch_bounds__(TPB, 1) fps_kernel(const float* __restrict__ x
   float* const sz = sm + 2 * SMEM_CAP;
   __shared__ int wsum[NW];
   __shared__ WinSlot slots[2][NW];
-  __shared__ int s_total;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long cloud = blockIdx.x;
@@ -233,6 +234,314 @@ __global__ void __launch_bounds__(TPB, 1) fps_kernel(const float* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pruned kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int CELLS = 4096;                       // 32 x 32 (Morton) x 4 grid over the eligible points' box
+constexpr int BUCKET = 128;                       // points per (warp, slot) = 32 lanes x 4
+constexpr int BUCKETS_MAX = NW * GROUPS_MAX;      // 256
+constexpr int PR_CAP = 17792;                     // points with smem-resident coordinates (139 buckets)
+constexpr int PR_REGION_A = 16384;                // cell counters in the prologue, then boxes + records + winner list
+constexpr int PR_ELIST = 1536;                    // winners kept in smem (compact positions); more samples spill to idx[]
+constexpr int PR_SMEM_BYTES = PR_CAP * 12 + PR_REGION_A;
+
+struct BucketRec { float maxT; int e; };            // best point of a bucket: its distance and compact position
+struct WinRec { unsigned val; int e; };
+
+__device__ __forceinline__ unsigned spread5(unsigned v) {        // abcde -> a0b0c0d0e (Morton spread)
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+__device__ __forceinline__ float warp_min_f(float v) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// comp layout per cloud (n128 = n rounded up to 128): x[n128] y[n128] z[n128] oidx[n128]
+__global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restrict__ xyz_all, int n, int m,
+                                                            int* __restrict__ idx_all, float* __restrict__ out_all,
+                                                            float* __restrict__ comp_all) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* const sx = reinterpret_cast<float*>(smraw);
+  float* const sy = sx + PR_CAP;
+  float* const sz = sy + PR_CAP;
+  unsigned char* const regionA = smraw + PR_CAP * 12;
+  int* const cells = reinterpret_cast<int*>(regionA);
+  float4* const blo = reinterpret_cast<float4*>(regionA);
+  float4* const bhi = blo + BUCKETS_MAX;
+  BucketRec* const rec = reinterpret_cast<BucketRec*>(bhi + BUCKETS_MAX);      // 8 KB + 2 KB
+  int* const elist = reinterpret_cast<int*>(rec + BUCKETS_MAX);                // 6 KB: 16 KB in all
+  __shared__ float red[NW][8];
+  __shared__ int wsum[NW];
+  __shared__ WinRec slots[2][NW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long cloud = blockIdx.x;
+  const float* const xyz = xyz_all + cloud * n * 3;
+  int* const idx = idx_all + cloud * m;
+  const int n128 = (n + BUCKET - 1) / BUCKET * BUCKET;
+  float* const cx = comp_all + cloud * 4 * n128;
+  float* const cy = cx + n128;
+  float* const cz = cy + n128;
+  int* const co = reinterpret_cast<int*>(cz + n128);
+  const float inf = __int_as_float(0x7f800000);
+
+  // tie key of the reference: (bitreverse_L(k mod T), k div T) as one integer
+  int L = 0;
+  while ((2 << L) <= n && L < 9) ++L;
+  const unsigned T = 1u << L, nq = (unsigned)((n + (int)T - 1) >> L);
+  auto tiekey = [&](int k) -> unsigned { return bitrev((unsigned)k & (T - 1), L) * nq + ((unsigned)k >> L); };
+
+  // ---- pass 1: eligibility, count, bounding box ----
+  int cnt = 0;
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  for (int k = tid; k < n; k += TPB) {
+    const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+    const float mag = fmaf(z, z, fmaf(x, x, y * y));
+    if (!((double)mag <= 1e-3)) {
+      ++cnt;
+      lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+      hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+    }
+  }
+  #pragma unroll
+  for (int a = 0; a < 3; ++a) { lo[a] = warp_min_f(lo[a]); hi[a] = warp_max_f(hi[a]); }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) {
+    red[warp][0] = lo[0]; red[warp][1] = lo[1]; red[warp][2] = lo[2];
+    red[warp][3] = hi[0]; red[warp][4] = hi[1]; red[warp][5] = hi[2];
+    wsum[warp] = cnt;
+  }
+  for (int c = tid; c < CELLS; c += TPB) cells[c] = 0;
+  __syncthreads();
+  int E = 0;
+  #pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    E += wsum[w];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], red[w][a]); hi[a] = fmaxf(hi[a], red[w][3 + a]); }
+  }
+
+  if (tid == 0) idx[0] = 0;
+  if (E == 0) {                          // nothing eligible: the reference returns index 0 throughout
+    for (int j = 1 + tid; j < m; j += TPB) idx[j] = 0;
+  } else {
+    // ---- pass 2/3: counting sort by grid cell (order inside a cell is irrelevant for the result) ----
+    const float sxs = hi[0] > lo[0] ? 32.0f / (hi[0] - lo[0]) : 0.0f;
+    const float sys = hi[1] > lo[1] ? 32.0f / (hi[1] - lo[1]) : 0.0f;
+    const float szs = hi[2] > lo[2] ? 4.0f / (hi[2] - lo[2]) : 0.0f;
+    auto cell_of = [&](float x, float y, float z) -> int {
+      const int ix = min(31, max(0, (int)((x - lo[0]) * sxs)));
+      const int iy = min(31, max(0, (int)((y - lo[1]) * sys)));
+      const int iz = min(3, max(0, (int)((z - lo[2]) * szs)));
+      return (int)(((spread5((unsigned)ix) | (spread5((unsigned)iy) << 1)) << 2) | (unsigned)iz);
+    };
+    for (int k = tid; k < n; k += TPB) {
+      const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+      const float mag = fmaf(z, z, fmaf(x, x, y * y));
+      if (!((double)mag <= 1e-3)) atomicAdd(&cells[cell_of(x, y, z)], 1);
+    }
+    __syncthreads();
+    {
+      constexpr int PER = CELLS / TPB;     // 8 consecutive cells per thread
+      int loc[PER], sum = 0;
+      #pragma unroll
+      for (int c = 0; c < PER; ++c) { loc[c] = cells[tid * PER + c]; sum += loc[c]; }
+      int total;
+      int base = block_exscan(sum, &total, wsum);
+      #pragma unroll
+      for (int c = 0; c < PER; ++c) { cells[tid * PER + c] = base; base += loc[c]; }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += TPB) {
+      const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+      const float mag = fmaf(z, z, fmaf(x, x, y * y));
+      if (!((double)mag <= 1e-3)) {
+        const int e = atomicAdd(&cells[cell_of(x, y, z)], 1);
+        cx[e] = x; cy[e] = y; cz[e] = z; co[e] = k;
+        if (e < PR_CAP) { sx[e] = x; sy[e] = y; sz[e] = z; }
+      }
+    }
+    const int E_pad = (E + BUCKET - 1) / BUCKET * BUCKET;
+    if (tid < E_pad - E) {               // fill the last bucket; padding never wins (distance -1) nor widens a box
+      const int e = E + tid;
+      cx[e] = 0.f; cy[e] = 0.f; cz[e] = 0.f; co[e] = 0;
+      if (e < PR_CAP) { sx[e] = 0.f; sy[e] = 0.f; sz[e] = 0.f; }
+    }
+    __threadfence_block();
+    __syncthreads();                     // cell counters are dead from here on: region A becomes boxes + records
+
+    const int nb = E_pad / BUCKET;       // buckets in use; bucket b = slot * NW + warp
+
+    auto load_group = [&](int e0, float4& px, float4& py, float4& pz) {
+      if (e0 < PR_CAP) {
+        px = *reinterpret_cast<const float4*>(sx + e0);
+        py = *reinterpret_cast<const float4*>(sy + e0);
+        pz = *reinterpret_cast<const float4*>(sz + e0);
+      } else {
+        px = *reinterpret_cast<const float4*>(cx + e0);
+        py = *reinterpret_cast<const float4*>(cy + e0);
+        pz = *reinterpret_cast<const float4*>(cz + e0);
+      }
+    };
+
+    // ---- bucket boxes, initial records, register-resident distances ----
+    float temp[GROUPS_MAX][4];
+    #pragma unroll
+    for (int i = 0; i < GROUPS_MAX; ++i) {
+      const int b = i * NW + warp;
+      const int e0 = 4 * (i * TPB + tid);
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) temp[i][q] = (e0 + q < E) ? 1e10f : -1.0f;
+      if (b < nb) {                      // warp-uniform
+        float4 px, py, pz;
+        load_group(e0, px, py, pz);
+        const float X[4] = {px.x, px.y, px.z, px.w}, Y[4] = {py.x, py.y, py.z, py.w}, Z[4] = {pz.x, pz.y, pz.z, pz.w};
+        float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (e0 + q < E) {
+            l0 = fminf(l0, X[q]); l1 = fminf(l1, Y[q]); l2 = fminf(l2, Z[q]);
+            h0 = fmaxf(h0, X[q]); h1 = fmaxf(h1, Y[q]); h2 = fmaxf(h2, Z[q]);
+          }
+        }
+        l0 = warp_min_f(l0); l1 = warp_min_f(l1); l2 = warp_min_f(l2);
+        h0 = warp_max_f(h0); h1 = warp_max_f(h1); h2 = warp_max_f(h2);
+        if (lane == 0) {
+          blo[b] = make_float4(l0, l1, l2, 0.f); bhi[b] = make_float4(h0, h1, h2, 0.f);
+          rec[b] = BucketRec{1e10f, e0};      // every bucket is touched in iteration 1 (LB < 1e10) before this is read
+        }
+      }
+    }
+    __syncthreads();
+
+    float ccx = xyz[0], ccy = xyz[1], ccz = xyz[2];       // centre of the first iteration: point 0 as given
+    for (int j = 1; j < m; ++j) {
+      // (a) one bucket per lane: can the new centre lower any distance in it?
+      const int btest = lane * NW + warp;                       // slot `lane` of this warp
+      const bool bvalid = lane < GROUPS_MAX && btest < nb;
+      const int bsafe = bvalid ? btest : warp;                  // bucket `warp` (slot 0) always exists when it matters
+      bool upd;
+      {
+        const float4 l4 = blo[bsafe], h4 = bhi[bsafe];
+        const float mt = rec[bsafe].maxT;
+        const float gx = max3(0.0f, l4.x - ccx, ccx - h4.x);
+        const float gy = max3(0.0f, l4.y - ccy, ccy - h4.y);
+        const float gz = max3(0.0f, l4.z - ccz, ccz - h4.z);
+        const float lb = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy)));   // <= d(k) for every k in the box
+        upd = bvalid && lb < mt;
+      }
+      const unsigned need = __ballot_sync(0xffffffffu, upd);
+
+      // (b) update the buckets that may change and re-elect their best point. Distances live in
+      //     registers, so the slot is selected through a jump table instead of 16 predicated blocks.
+      const f32x2 c2x = pack2(ccx, ccx), c2y = pack2(ccy, ccy), c2z = pack2(ccz, ccz);
+      auto update = [&](int i, float (&tq)[4]) {
+        const int e0 = 4 * (i * TPB + tid);
+        float4 px, py, pz;
+        load_group(e0, px, py, pz);
+        const f32x2 dx0 = sub2(pack2(px.x, px.y), c2x), dx1 = sub2(pack2(px.z, px.w), c2x);
+        const f32x2 dy0 = sub2(pack2(py.x, py.y), c2y), dy1 = sub2(pack2(py.z, py.w), c2y);
+        const f32x2 dz0 = sub2(pack2(pz.x, pz.y), c2z), dz1 = sub2(pack2(pz.z, pz.w), c2z);
+        const f32x2 d0 = fma2(dz0, dz0, fma2(dx0, dx0, mul2(dy0, dy0)));
+        const f32x2 d1 = fma2(dz1, dz1, fma2(dx1, dx1, mul2(dy1, dy1)));
+        float d[4];
+        unpack2(d0, d[0], d[1]);
+        unpack2(d1, d[2], d[3]);
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) tq[q] = fminf(d[q], tq[q]);
+        const float m4 = fmaxf(fmaxf(tq[0], tq[1]), fmaxf(tq[2], tq[3]));
+        const unsigned vb = m4 < 0.f ? 0u : __float_as_uint(m4);          // padding (-1) never competes
+        const unsigned vmax = __reduce_max_sync(0xffffffffu, vb);
+        // candidates: real points whose distance equals the bucket maximum
+        unsigned cm = 0u;
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) cm |= (e0 + q < E && __float_as_uint(tq[q]) == vmax) ? (1u << q) : 0u;
+        const unsigned lanes = __ballot_sync(0xffffffffu, cm != 0u);
+        const unsigned multi = __ballot_sync(0xffffffffu, (cm & (cm - 1)) != 0u);
+        int ebest = e0 + __ffs(cm) - 1;
+        if ((lanes & (lanes - 1)) != 0u || multi != 0u) {                 // warp-uniform; rare: exact tie -> the reference's key decides
+          unsigned lk = 0xffffffffu;
+          #pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (cm & (1u << q)) {
+              const unsigned key = tiekey(co[e0 + q]);
+              if (key < lk) { lk = key; ebest = e0 + q; }
+            }
+          }
+          const unsigned kmin = __reduce_min_sync(0xffffffffu, lk);
+          if (lk == kmin && cm != 0u) rec[i * NW + warp] = BucketRec{__uint_as_float(vmax), ebest};
+        } else if (cm != 0u) {
+          rec[i * NW + warp] = BucketRec{__uint_as_float(vmax), ebest};
+        }
+      };
+      for (unsigned todo = need; todo != 0u; todo &= todo - 1u) {          // warp-uniform
+        switch (__ffs(todo) - 1) {
+          case 0: update(0, temp[0]); break;    case 1: update(1, temp[1]); break;
+          case 2: update(2, temp[2]); break;    case 3: update(3, temp[3]); break;
+          case 4: update(4, temp[4]); break;    case 5: update(5, temp[5]); break;
+          case 6: update(6, temp[6]); break;    case 7: update(7, temp[7]); break;
+          case 8: update(8, temp[8]); break;    case 9: update(9, temp[9]); break;
+          case 10: update(10, temp[10]); break; case 11: update(11, temp[11]); break;
+          case 12: update(12, temp[12]); break; case 13: update(13, temp[13]); break;
+          case 14: update(14, temp[14]); break; default: update(15, temp[15]); break;
+        }
+      }
+      __syncwarp();
+
+      // (c) best bucket of this warp, (d) best warp of the block; ties go through the key (rare)
+      const BucketRec rr = rec[bsafe];
+      const unsigned vb = bvalid ? __float_as_uint(rr.maxT) : 0u;           // maxT >= 0 for every bucket in use
+      int e = bvalid ? rr.e : -1;
+      const unsigned V = __reduce_max_sync(0xffffffffu, vb);
+      unsigned cand = __ballot_sync(0xffffffffu, e >= 0 && vb == V);
+      if ((cand & (cand - 1)) != 0u) {
+        const unsigned key = (e >= 0 && vb == V) ? tiekey(co[e]) : 0xffffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        cand = __ballot_sync(0xffffffffu, key == kmin);
+      }
+      e = __shfl_sync(0xffffffffu, e, __ffs(cand) - 1);
+      const int par = j & 1;
+      if (lane == 0) slots[par][warp] = WinRec{cand ? V : 0u, cand ? e : -1};
+      __syncthreads();
+      const WinRec s2 = slots[par][lane & (NW - 1)];
+      const unsigned VV = __reduce_max_sync(0xffffffffu, s2.val);
+      unsigned cand2 = __ballot_sync(0xffffffffu, lane < NW && s2.e >= 0 && s2.val == VV);
+      if ((cand2 & (cand2 - 1)) != 0u) {
+        const unsigned key = (lane < NW && s2.e >= 0 && s2.val == VV) ? tiekey(co[s2.e]) : 0xffffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        cand2 = __ballot_sync(0xffffffffu, key == kmin);
+      }
+      const int ew = __shfl_sync(0xffffffffu, s2.e, __ffs(cand2) - 1);
+      if (ew < PR_CAP) { ccx = sx[ew]; ccy = sy[ew]; ccz = sz[ew]; }
+      else { ccx = cx[ew]; ccy = cy[ew]; ccz = cz[ew]; }
+      if (tid == 0) { if (j < PR_ELIST) elist[j] = ew; else idx[j] = ew; }   // compact position; translated below
+    }
+    __threadfence_block();
+    __syncthreads();
+    for (int j = 1 + tid; j < m; j += TPB) idx[j] = co[j < PR_ELIST ? elist[j] : idx[j]];
+  }
+
+  if (out_all != nullptr) {                   // fused gather of the sampled points, (m,3) per cloud
+    __threadfence_block();
+    __syncthreads();
+    float* const out = out_all + cloud * m * 3;
+    for (int j = tid; j < m; j += TPB) {
+      const int k = idx[j];
+      out[3 * j] = xyz[3 * k]; out[3 * j + 1] = xyz[3 * k + 1]; out[3 * j + 2] = xyz[3 * k + 2];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ points, const int* __restrict__ idx,
                                                      int c, int n, int m, float* __restrict__ out) {
   const int i = blockIdx.z, l = blockIdx.y;
@@ -254,7 +563,7 @@ __global__ void __launch_bounds__(256) gather_grad_kernel(const float* __restric
 using namespace dusty;
 using namespace dusty::fps;
 
-static size_t fps_comp_bytes(int b, int n) { return align_up((size_t)b * 4 * ((n + 3) & ~3) * sizeof(float), 256); }
+static size_t fps_comp_bytes(int b, int n) { return align_up((size_t)b * 4 * ((n + 127) / 128 * 128) * sizeof(float), 256); }
 static size_t fps_temp_bytes(int b, int n) { return n > REG_CAP ? align_up((size_t)b * ((n + 3) & ~3) * sizeof(float), 256) : 0; }
 
 extern "C" size_t dusty_fps_workspace_bytes(int b, int n, int m) {
@@ -276,14 +585,19 @@ extern "C" int dusty_fps(const float* xyz, int b, int n, int m, int32_t* idx, fl
   float* comp = static_cast<float*>(workspace);
   float* temp = reinterpret_cast<float*>(static_cast<char*>(workspace) + fps_comp_bytes(b, n));
   static bool configured = false;
+  static bool force_flat = false;
   if (!configured) {
-    DUSTY_CUDA(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    DUSTY_CUDA(cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(fps_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
+    const char* env = getenv("DUSTY_FPS_FLAT");       // A/B switch for profiling; both kernels give the same indices
+    force_flat = env && env[0] == '1';
     configured = true;
   }
-  if (n <= REG_CAP) fps_kernel<true><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
-  else fps_kernel<false><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
-  DUSTY_AFTER_LAUNCH("fps_kernel");
+  if (n > REG_CAP) fps_flat_kernel<false><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
+  else if (force_flat) fps_flat_kernel<true><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
+  else fps_pruned_kernel<<<b, TPB, PR_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp);
+  DUSTY_AFTER_LAUNCH("fps kernel");
   return 0;
 }
 

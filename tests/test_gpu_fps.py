@@ -102,3 +102,14 @@ def test_against_reference_cuda_golden(golden):
         assert np.array_equal(fps_gpu(x, m), g[f"fps{i}_idx"]), g[f"fps{i}_case"]
         i += 1
     assert np.array_equal(fps_gpu(g["fps_deg_input"], 200), g["fps_deg_idx"])
+
+
+def test_duplicate_points_tie_inside_one_lane():
+    """Exact duplicates that land next to each other after the spatial sort: one lane then holds two
+    candidates with the same distance, the path where the tie key decides (and must stay warp-uniform)."""
+    base = lidar_like_clouds(2, 4000, 31, dropped=0.1, near=0.05)
+    x = np.repeat(base, 3, axis=1)                     # every point three times
+    assert np.array_equal(fps_gpu(x, 300), native.fps(x, 300))
+    y = lidar_like_clouds(300, 2048, 32, dropped=0.3, near=0.1)   # more clouds than SMs
+    y[:, 1::2] = y[:, ::2]                             # pairs of duplicates
+    assert np.array_equal(fps_gpu(y, 128), native.fps(y, 128))
