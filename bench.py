@@ -31,7 +31,10 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("DUSTY_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+if "DUSTY_NCCL_DEBUG" in os.environ:
+    os.environ["NCCL_DEBUG"] = os.environ["DUSTY_NCCL_DEBUG"]
+else:
+    os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version banner on stdout; keep stdout to the one JSON line
 
 N_CLOUDS = 1000          # per set (configs[2])
 N_POINTS = 2048

@@ -26,6 +26,12 @@ int fail_arg(int code, const char* fmt, ...) {
 
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 int check_device() {
   static thread_local int checked_dev = -1;
   int dev = 0;

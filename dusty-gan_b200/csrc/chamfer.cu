@@ -329,10 +329,11 @@ static int pick_r(int maxcount) {
 
 template <int R, bool MATRIX>
 static int launch_nn(const Params& p, dim3 grid, cudaStream_t st) {
-  static bool configured = false;   // per (R, MATRIX) instantiation
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // per (R, MATRIX) instantiation and device: the attribute is per context
+  const int dev = current_device();
+  if (!configured[dev]) {
     DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   nn_kernel<R, MATRIX><<<grid, TPB, SMEM_BYTES, st>>>(p);
   DUSTY_AFTER_LAUNCH("chamfer nn_kernel");

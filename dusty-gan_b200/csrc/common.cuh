@@ -14,6 +14,8 @@ int fail_cuda(cudaError_t e, const char* what);
 int fail_arg(int code, const char* fmt, ...);
 void count_launches(int n);
 int check_device();   // DUSTY_EARCH unless the current device is sm_10x
+int current_device();  // cudaGetDevice, clamped to [0, kMaxDevices)
+constexpr int kMaxDevices = 64;
 
 constexpr int kNumSMs = 148;
 

@@ -584,15 +584,16 @@ extern "C" int dusty_fps(const float* xyz, int b, int n, int m, int32_t* idx, fl
     return fail_arg(DUSTY_ENOSPACE, "fps: workspace %zu < %zu", workspace_bytes, dusty_fps_workspace_bytes(b, n, m));
   float* comp = static_cast<float*>(workspace);
   float* temp = reinterpret_cast<float*>(static_cast<char*>(workspace) + fps_comp_bytes(b, n));
-  static bool configured = false;
+  static bool configured[kMaxDevices] = {};
   static bool force_flat = false;
-  if (!configured) {
+  const int dev = current_device();
+  if (!configured[dev]) {
     DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DUSTY_CUDA(cudaFuncSetAttribute(fps_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
     const char* env = getenv("DUSTY_FPS_FLAT");       // A/B switch for profiling; both kernels give the same indices
     force_flat = env && env[0] == '1';
-    configured = true;
+    configured[dev] = true;
   }
   if (n > REG_CAP) fps_flat_kernel<false><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
   else if (force_flat) fps_flat_kernel<true><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);

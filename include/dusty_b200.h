@@ -17,6 +17,8 @@
  *   dusty_chamfer_matrix         utils/metrics/cov_mmd_1nna.py:24-51 (_pairwise_distance, the Python
  *                                double loop over compute_cd, :19-21)
  *   dusty_cov_mmd_1nna_finalize  utils/metrics/cov_mmd_1nna.py:54-106 (_compute_cov_mmd, _compute_nna k=1)
+ *   dusty_jsd_vote, dusty_jsd_from_counts   utils/metrics/jsd.py:23-92, 110-121 (entropy_of_occupancy_grid,
+ *                                _jensen_shannon_divergence)
  *   dusty_fps                    utils/sampling/fps/furthest_point_sampling.cpp:79-100
  *                                -> furthest_point_sampling_kernel_wrapper, furthest_point_sampling.cu:209-260
  *   dusty_gather_points          utils/sampling/fps/furthest_point_sampling.cpp:27-50
@@ -123,6 +125,24 @@ DUSTY_API int dusty_chamfer_matrix(const float* A, int na, int pa, const float* 
 DUSTY_API size_t dusty_cov_mmd_1nna_workspace_bytes(int nr, int ng);
 DUSTY_API int dusty_cov_mmd_1nna_finalize(const float* Mrr, const float* Mrg, const float* Mgg, int nr, int ng,
                                 float* out7, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * JSD between occupancy histograms (next row 8f-2; reference utils/metrics/jsd.py:23-121)
+ * -------------------------------------------------------------------------------------------- */
+
+/* Every point of pcs (b,npts,3) votes for its nearest in-sphere grid point (f32 arithmetic and
+ * lowest-index tie rule of the reference's brute-force arg-min, jsd.py:59-69). The grid is supplied
+ * by the caller exactly as the reference builds it (jsd.py:10-20): grid (ng,3) the in-sphere points
+ * in order, cell_to_idx (res^3) their compact index or -1, axis (res) the coordinates along one axis.
+ * counters (ng) u32: points per grid point (grid_counters); clouds_touching (ng) u32: number of
+ * clouds with at least one point there (grid_bernoulli_rvars). Both are overwritten. */
+DUSTY_API int dusty_jsd_vote(const float* pcs, int b, int npts, int resolution, int ng, const float* grid,
+                             const int32_t* cell_to_idx, const float* axis, float spacing,
+                             uint32_t* counters, uint32_t* clouds_touching, void* stream);
+
+/* _jensen_shannon_divergence of two count vectors (jsd.py:110-121), base-2 entropies; out[0] f32. */
+DUSTY_API int dusty_jsd_from_counts(const uint32_t* counts_p, const uint32_t* counts_q, int ng, float* out,
+                                    void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Farthest-point sampling

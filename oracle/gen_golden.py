@@ -52,7 +52,8 @@ def import_reference():
     # `from .cd.chamfer_distance import *` re-exports the extension handle `cd`, shadowing the sub-package
     ref_cd = sys.modules["utils.metrics.distance.cd.chamfer_distance"]
     import utils as ref_utils
-    return ref_dusty, ref_lidar, ref_metrics, ref_cd, ref_utils
+    import utils.metrics.jsd as ref_jsd
+    return ref_dusty, ref_lidar, ref_metrics, ref_cd, ref_utils, ref_jsd
 
 
 def hdl64e_angles():
@@ -69,7 +70,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
     torch.set_num_threads(1)
-    ref_dusty, ref_lidar, ref_metrics, ref_cd, ref_utils = import_reference()
+    ref_dusty, ref_lidar, ref_metrics, ref_cd, ref_utils, ref_jsd = import_reference()
     B, H, W = 3, 16, 64
     g = torch.Generator().manual_seed(1234)
 
@@ -172,6 +173,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "metrics_cpu.npz"), ref=np_(ref), gen=np_(gen), M_rr=np_(M_rr), M_rg=np_(M_rg),
                         M_gg=np_(M_gg), gen_dup=np_(gen_dup), M_rg_dup=np_(M_rg_dup), score_keys=np.array(keys),
                         score_values=np.array([scores[k] for k in keys], np.float64))
+    # ---------------- JSD (next row 8f-2): the reference's own voting and divergence ----------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import lidar_like_clouds
+    gen_j = torch.from_numpy(lidar_like_clouds(6, 700, 41, dropped=0.1, near=0.1)) / 2.0       # evaluate_synthesis.py:174-177 halves
+    ref_j = torch.from_numpy(lidar_like_clouds(5, 700, 42, dropped=0.1, near=0.1)) / 2.0
+    gen_j[0, :4] = torch.tensor([[0.5, 0.0, 0.0], [-0.5, 0.0, 0.0], [0.2887, 0.2887, 0.2887], [0.0185185, 0.0185185, 0.0]])
+    ref_j[0, :3] = torch.tensor([[0.6, 0.1, 0.0], [0.0, 0.0, 0.52], [-0.3, 0.41, 0.1]])           # outside the sphere
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ent_g, cnt_g = ref_jsd.entropy_of_occupancy_grid(gen_j, 28, True, 128, False)
+        ent_r, cnt_r = ref_jsd.entropy_of_occupancy_grid(ref_j, 28, True, 128, False)
+        jsd = ref_jsd.compute_jsd(gen_j, ref_j, verbose=False)
+        grid, spacing = ref_jsd.unit_cube_grid_point_cloud(28, True, "cpu")
+    np.savez_compressed(os.path.join(OUT, "jsd_cpu.npz"), gen=np_(gen_j), ref=np_(ref_j), counters_gen=np_(cnt_g),
+                        counters_ref=np_(cnt_r), entropy_gen=np.float64(ent_g.item()), entropy_ref=np.float64(ent_r.item()),
+                        jsd=np.float64(jsd), grid=np_(grid))
     print("wrote", sorted(os.listdir(OUT)))
 
 

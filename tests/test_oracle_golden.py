@@ -169,3 +169,16 @@ def test_chamfer_cuda_rounding_matches_reference_cuda_kernel_outputs(golden):
         d1, d2, i1, i2 = native.chamfer_forward(a, c, rounding="cuda")
         assert np.array_equal(d1, g[f"cd{i}_dist1"]) and np.array_equal(d2, g[f"cd{i}_dist2"])
         assert np.array_equal(i1, g[f"cd{i}_idx1"]) and np.array_equal(i2, g[f"cd{i}_idx2"])
+
+
+# ---- JSD (next row 8f-2) ----
+def test_jsd_oracle_matches_reference(golden):
+    from oracle import jsd as oj
+    g = golden("jsd_cpu.npz")
+    grid, spacing = oj.grid_points(28, True)
+    assert np.array_equal(grid, g["grid"])
+    cg, tg = oj.vote(g["gen"]); cr, tr = oj.vote(g["ref"])
+    assert np.array_equal(cg, g["counters_gen"].astype(np.int64)) and np.array_equal(cr, g["counters_ref"].astype(np.int64))
+    assert cg.sum() == g["gen"].shape[0] * g["gen"].shape[1]
+    assert oj.jsd_from_counts(cg, cr) == pytest.approx(float(g["jsd"]), rel=1e-5)
+    assert oj.compute_jsd(g["gen"], g["ref"]) == pytest.approx(float(g["jsd"]), rel=1e-5)
