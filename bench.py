@@ -264,10 +264,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rng_a = synthetic_cpu_clouds(64, 1); rng_b = synthetic_cpu_clouds(64, 2)
+    rng_a = synthetic_cpu_clouds(max(64, os.cpu_count() or 1), 1); rng_b = synthetic_cpu_clouds(64, 2)
     cores = os.cpu_count() or 1
     rows = max(cores, 16)
-    cols = 32
+    cols = 64          # 16 x 64 = 1024 entries (~1-4 s per step on 16-8 cores)
     vals = []
     t_all = time.perf_counter()
     kind = "reference"

@@ -87,6 +87,7 @@ template <int C, bool COMPACT>
 __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
   __shared__ int wsum[2][TPB / 32];
   __shared__ int s_base;
+  __shared__ __align__(16) float xyz_stage[TPB / 32][384];     // per-warp transpose buffer for interleaved points
   const dusty_head_params& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long img = blockIdx.x / a.segs_per_image;
@@ -178,10 +179,26 @@ __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
           stg_stream(reinterpret_cast<float4*>(o + npix), ys[it]);
           stg_stream(reinterpret_cast<float4*>(o + 2 * npix), zs[it]);
         } else {
-          float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + pix) * 3);
-          stg_stream(o, make_float4(X[0], Y[0], Z[0], X[1]));
-          stg_stream(o + 1, make_float4(Y[1], Z[1], X[2], Y[2]));
-          stg_stream(o + 2, make_float4(Z[2], X[3], Y[3], Z[3]));
+          const int wpix = seg * SEG + it * (TPB * 4) + warp * 128;       // first pixel of this warp's 128
+          if (wpix + 128 <= npix) {
+            // whole warp in range (uniform): transpose through shared memory so that every STG.128 of
+            // the warp covers 512 contiguous bytes instead of 16 bytes out of every 48
+            float4* stage = reinterpret_cast<float4*>(xyz_stage[warp]);
+            stage[lane * 3] = make_float4(X[0], Y[0], Z[0], X[1]);
+            stage[lane * 3 + 1] = make_float4(Y[1], Z[1], X[2], Y[2]);
+            stage[lane * 3 + 2] = make_float4(Z[2], X[3], Y[3], Z[3]);
+            __syncwarp();
+            float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + wpix) * 3);
+            stg_stream(o + lane, stage[lane]);
+            stg_stream(o + lane + 32, stage[lane + 32]);
+            stg_stream(o + lane + 64, stage[lane + 64]);
+            __syncwarp();
+          } else {
+            float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + pix) * 3);
+            stg_stream(o, make_float4(X[0], Y[0], Z[0], X[1]));
+            stg_stream(o + 1, make_float4(Y[1], Z[1], X[2], Y[2]));
+            stg_stream(o + 2, make_float4(Z[2], X[3], Y[3], Z[3]));
+          }
         }
       }
       tcount += __popc(vbits[it]);
