@@ -542,6 +542,278 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pruned kernel, throughput variant: same algorithm, but nothing large is on chip. Coordinates and
+// running distances stay in the L2-resident workspace (a pruned iteration touches ~6 % of them),
+// only the bucket boxes/records live in shared memory, so four clouds share one SM and overlap
+// each other's per-iteration latency chain (prune test -> update -> REDUX -> barrier -> REDUX).
+// Records carry the winner's coordinates so the next centre never costs an L2 round trip.
+// ------------------------------------------------------------------------------------------------
+constexpr int MT_TPB = 256;
+constexpr int MT_NW = MT_TPB / 32;                 // 8 warps; lane l of a warp tests the warp's slot l
+constexpr int MT_BUCKETS = MT_NW * 32;             // 256 buckets = 32768 points
+constexpr int MT_ELIST = 1536;
+constexpr int MT_SMEM_BYTES = MT_BUCKETS * (16 + 16 + 32) + MT_ELIST * 4;   // boxes + records + winner list = 22 KB
+static_assert(MT_SMEM_BYTES >= CELLS * 4, "the cell counters alias the box/record region");
+
+struct MtRec { float maxT; int e; float x, y, z; float pad0, pad1, pad2; };   // 32 B
+struct MtWin { unsigned val; int e; float x, y, z; };
+
+// comp layout per cloud: x[n128] y[n128] z[n128] oidx[n128]; dist_all: t[n128]
+__global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __restrict__ xyz_all, int n, int m,
+                                                              int* __restrict__ idx_all, float* __restrict__ out_all,
+                                                              float* __restrict__ comp_all, float* __restrict__ dist_all) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  int* const cells = reinterpret_cast<int*>(smraw);
+  float4* const blo = reinterpret_cast<float4*>(smraw);
+  float4* const bhi = blo + MT_BUCKETS;
+  MtRec* const rec = reinterpret_cast<MtRec*>(bhi + MT_BUCKETS);
+  int* const elist = reinterpret_cast<int*>(rec + MT_BUCKETS);
+  __shared__ float red[MT_NW][8];
+  __shared__ int wsum[MT_NW];
+  __shared__ MtWin slots[2][MT_NW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long cloud = blockIdx.x;
+  const float* const xyz = xyz_all + cloud * n * 3;
+  int* const idx = idx_all + cloud * m;
+  const int n128 = (n + BUCKET - 1) / BUCKET * BUCKET;
+  float* const cx = comp_all + cloud * 4 * n128;
+  float* const cy = cx + n128;
+  float* const cz = cy + n128;
+  int* const co = reinterpret_cast<int*>(cz + n128);
+  float* const ct = dist_all + cloud * n128;
+  const float inf = __int_as_float(0x7f800000);
+
+  int L = 0;
+  while ((2 << L) <= n && L < 9) ++L;
+  const unsigned T = 1u << L, nq = (unsigned)((n + (int)T - 1) >> L);
+  auto tiekey = [&](int k) -> unsigned { return bitrev((unsigned)k & (T - 1), L) * nq + ((unsigned)k >> L); };
+
+  // ---- pass 1: eligibility, count, bounding box ----
+  int cnt = 0;
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  for (int k = tid; k < n; k += MT_TPB) {
+    const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+    const float mag = fmaf(z, z, fmaf(x, x, y * y));
+    if (!((double)mag <= 1e-3)) {
+      ++cnt;
+      lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+      hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+    }
+  }
+  #pragma unroll
+  for (int a = 0; a < 3; ++a) { lo[a] = warp_min_f(lo[a]); hi[a] = warp_max_f(hi[a]); }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) {
+    red[warp][0] = lo[0]; red[warp][1] = lo[1]; red[warp][2] = lo[2];
+    red[warp][3] = hi[0]; red[warp][4] = hi[1]; red[warp][5] = hi[2];
+    wsum[warp] = cnt;
+  }
+  for (int c = tid; c < CELLS; c += MT_TPB) cells[c] = 0;
+  __syncthreads();
+  int E = 0;
+  #pragma unroll
+  for (int w = 0; w < MT_NW; ++w) {
+    E += wsum[w];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], red[w][a]); hi[a] = fmaxf(hi[a], red[w][3 + a]); }
+  }
+  __syncthreads();
+
+  if (tid == 0) idx[0] = 0;
+  if (E == 0) {
+    for (int j = 1 + tid; j < m; j += MT_TPB) idx[j] = 0;
+  } else {
+    // ---- counting sort by grid cell into the workspace ----
+    const float sxs = hi[0] > lo[0] ? 32.0f / (hi[0] - lo[0]) : 0.0f;
+    const float sys = hi[1] > lo[1] ? 32.0f / (hi[1] - lo[1]) : 0.0f;
+    const float szs = hi[2] > lo[2] ? 4.0f / (hi[2] - lo[2]) : 0.0f;
+    auto cell_of = [&](float x, float y, float z) -> int {
+      const int ix = min(31, max(0, (int)((x - lo[0]) * sxs)));
+      const int iy = min(31, max(0, (int)((y - lo[1]) * sys)));
+      const int iz = min(3, max(0, (int)((z - lo[2]) * szs)));
+      return (int)(((spread5((unsigned)ix) | (spread5((unsigned)iy) << 1)) << 2) | (unsigned)iz);
+    };
+    for (int k = tid; k < n; k += MT_TPB) {
+      const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+      const float mag = fmaf(z, z, fmaf(x, x, y * y));
+      if (!((double)mag <= 1e-3)) atomicAdd(&cells[cell_of(x, y, z)], 1);
+    }
+    __syncthreads();
+    {
+      constexpr int PER = CELLS / MT_TPB;     // 16 consecutive cells per thread
+      int sum = 0;
+      #pragma unroll
+      for (int c = 0; c < PER; ++c) sum += cells[tid * PER + c];
+      // block exclusive scan over 256 threads
+      int inc = sum;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      int base = inc - sum;
+      #pragma unroll
+      for (int w = 0; w < MT_NW; ++w) if (w < warp) base += wsum[w];
+      #pragma unroll
+      for (int c = 0; c < PER; ++c) { const int v = cells[tid * PER + c]; cells[tid * PER + c] = base; base += v; }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += MT_TPB) {
+      const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+      const float mag = fmaf(z, z, fmaf(x, x, y * y));
+      if (!((double)mag <= 1e-3)) {
+        const int e = atomicAdd(&cells[cell_of(x, y, z)], 1);
+        cx[e] = x; cy[e] = y; cz[e] = z; co[e] = k; ct[e] = 1e10f;
+      }
+    }
+    const int E_pad = (E + BUCKET - 1) / BUCKET * BUCKET;
+    if (tid < E_pad - E) {
+      const int e = E + tid;
+      cx[e] = 0.f; cy[e] = 0.f; cz[e] = 0.f; co[e] = 0; ct[e] = -1.0f;
+    }
+    __threadfence_block();
+    __syncthreads();                     // cell counters are dead: the region becomes boxes + records
+
+    const int nb = E_pad / BUCKET;       // bucket b = slot * MT_NW + warp; points [128 b, 128 b + 128)
+
+    for (int b = warp; b < nb; b += MT_NW) {
+      const int e0 = b * BUCKET + 4 * lane;
+      const float4 px = *reinterpret_cast<const float4*>(cx + e0);
+      const float4 py = *reinterpret_cast<const float4*>(cy + e0);
+      const float4 pz = *reinterpret_cast<const float4*>(cz + e0);
+      const float X[4] = {px.x, px.y, px.z, px.w}, Y[4] = {py.x, py.y, py.z, py.w}, Z[4] = {pz.x, pz.y, pz.z, pz.w};
+      float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (e0 + q < E) {
+          l0 = fminf(l0, X[q]); l1 = fminf(l1, Y[q]); l2 = fminf(l2, Z[q]);
+          h0 = fmaxf(h0, X[q]); h1 = fmaxf(h1, Y[q]); h2 = fmaxf(h2, Z[q]);
+        }
+      }
+      l0 = warp_min_f(l0); l1 = warp_min_f(l1); l2 = warp_min_f(l2);
+      h0 = warp_max_f(h0); h1 = warp_max_f(h1); h2 = warp_max_f(h2);
+      if (lane == 0) {
+        blo[b] = make_float4(l0, l1, l2, 0.f); bhi[b] = make_float4(h0, h1, h2, 0.f);
+        rec[b] = MtRec{1e10f, e0, X[0], Y[0], Z[0], 0.f, 0.f, 0.f};   // replaced in iteration 1 (LB < 1e10 everywhere)
+      }
+    }
+    __syncthreads();
+
+    float ccx = xyz[0], ccy = xyz[1], ccz = xyz[2];
+    for (int j = 1; j < m; ++j) {
+      // (a) lane l tests the warp's slot l
+      const int btest = lane * MT_NW + warp;
+      const bool bvalid = btest < nb;
+      const int bsafe = bvalid ? btest : 0;
+      bool upd;
+      {
+        const float4 l4 = blo[bsafe], h4 = bhi[bsafe];
+        const float mt = rec[bsafe].maxT;
+        const float gx = max3(0.0f, l4.x - ccx, ccx - h4.x);
+        const float gy = max3(0.0f, l4.y - ccy, ccy - h4.y);
+        const float gz = max3(0.0f, l4.z - ccz, ccz - h4.z);
+        const float lb = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy)));
+        upd = bvalid && lb < mt;
+      }
+      const unsigned need = __ballot_sync(0xffffffffu, upd);
+
+      // (b) update the buckets that may change
+      const f32x2 c2x = pack2(ccx, ccx), c2y = pack2(ccy, ccy), c2z = pack2(ccz, ccz);
+      for (unsigned todo = need; todo != 0u; todo &= todo - 1u) {
+        const int b = (__ffs(todo) - 1) * MT_NW + warp;
+        const int e0 = b * BUCKET + 4 * lane;
+        const float4 px = *reinterpret_cast<const float4*>(cx + e0);
+        const float4 py = *reinterpret_cast<const float4*>(cy + e0);
+        const float4 pz = *reinterpret_cast<const float4*>(cz + e0);
+        const float4 t4 = *reinterpret_cast<const float4*>(ct + e0);
+        const f32x2 dx0 = sub2(pack2(px.x, px.y), c2x), dx1 = sub2(pack2(px.z, px.w), c2x);
+        const f32x2 dy0 = sub2(pack2(py.x, py.y), c2y), dy1 = sub2(pack2(py.z, py.w), c2y);
+        const f32x2 dz0 = sub2(pack2(pz.x, pz.y), c2z), dz1 = sub2(pack2(pz.z, pz.w), c2z);
+        const f32x2 d0 = fma2(dz0, dz0, fma2(dx0, dx0, mul2(dy0, dy0)));
+        const f32x2 d1 = fma2(dz1, dz1, fma2(dx1, dx1, mul2(dy1, dy1)));
+        float d[4];
+        unpack2(d0, d[0], d[1]);
+        unpack2(d1, d[2], d[3]);
+        float tq[4] = {fminf(d[0], t4.x), fminf(d[1], t4.y), fminf(d[2], t4.z), fminf(d[3], t4.w)};
+        *reinterpret_cast<float4*>(ct + e0) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+        const float m4 = fmaxf(fmaxf(tq[0], tq[1]), fmaxf(tq[2], tq[3]));
+        const unsigned vb = m4 < 0.f ? 0u : __float_as_uint(m4);
+        const unsigned vmax = __reduce_max_sync(0xffffffffu, vb);
+        unsigned cm = 0u;
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) cm |= (e0 + q < E && __float_as_uint(tq[q]) == vmax) ? (1u << q) : 0u;
+        const unsigned lanes = __ballot_sync(0xffffffffu, cm != 0u);
+        const unsigned multi = __ballot_sync(0xffffffffu, (cm & (cm - 1)) != 0u);
+        int qb = __ffs(cm) - 1;
+        bool mine = cm != 0u;
+        if ((lanes & (lanes - 1)) != 0u || multi != 0u) {       // warp-uniform; exact tie: the reference's key decides
+          unsigned lk = 0xffffffffu;
+          #pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (cm & (1u << q)) {
+              const unsigned key = tiekey(co[e0 + q]);
+              if (key < lk) { lk = key; qb = q; }
+            }
+          }
+          const unsigned kmin = __reduce_min_sync(0xffffffffu, lk);
+          mine = cm != 0u && lk == kmin;
+        }
+        if (mine) {
+          const float wx = qb == 0 ? px.x : qb == 1 ? px.y : qb == 2 ? px.z : px.w;
+          const float wy = qb == 0 ? py.x : qb == 1 ? py.y : qb == 2 ? py.z : py.w;
+          const float wz = qb == 0 ? pz.x : qb == 1 ? pz.y : qb == 2 ? pz.z : pz.w;
+          rec[b] = MtRec{__uint_as_float(vmax), e0 + qb, wx, wy, wz, 0.f, 0.f, 0.f};
+        }
+      }
+      __syncwarp();
+
+      // (c) best bucket of this warp, (d) best warp of the block
+      const MtRec rr = rec[bsafe];
+      const unsigned vb = bvalid ? __float_as_uint(rr.maxT) : 0u;
+      const unsigned V = __reduce_max_sync(0xffffffffu, vb);
+      unsigned cand = __ballot_sync(0xffffffffu, bvalid && vb == V);
+      if ((cand & (cand - 1)) != 0u) {
+        const unsigned key = (bvalid && vb == V) ? tiekey(co[rr.e]) : 0xffffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        cand = __ballot_sync(0xffffffffu, key == kmin);
+      }
+      const int par = j & 1;
+      if (cand == 0u) { if (lane == 0) slots[par][warp] = MtWin{0u, -1, 0.f, 0.f, 0.f}; }
+      else if (lane == __ffs(cand) - 1) slots[par][warp] = MtWin{V, rr.e, rr.x, rr.y, rr.z};
+      __syncthreads();
+      const MtWin s2 = slots[par][lane & (MT_NW - 1)];
+      const bool sv = lane < MT_NW && s2.e >= 0;
+      const unsigned VV = __reduce_max_sync(0xffffffffu, sv ? s2.val : 0u);
+      unsigned cand2 = __ballot_sync(0xffffffffu, sv && s2.val == VV);
+      if ((cand2 & (cand2 - 1)) != 0u) {
+        const unsigned key = (sv && s2.val == VV) ? tiekey(co[s2.e]) : 0xffffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        cand2 = __ballot_sync(0xffffffffu, key == kmin);
+      }
+      const int src = __ffs(cand2) - 1;
+      const int ew = __shfl_sync(0xffffffffu, s2.e, src);
+      ccx = __shfl_sync(0xffffffffu, s2.x, src);
+      ccy = __shfl_sync(0xffffffffu, s2.y, src);
+      ccz = __shfl_sync(0xffffffffu, s2.z, src);
+      if (tid == 0) { if (j < MT_ELIST) elist[j] = ew; else idx[j] = ew; }
+    }
+    __threadfence_block();
+    __syncthreads();
+    for (int j = 1 + tid; j < m; j += MT_TPB) idx[j] = co[j < MT_ELIST ? elist[j] : idx[j]];
+  }
+
+  if (out_all != nullptr) {
+    __threadfence_block();
+    __syncthreads();
+    float* const out = out_all + cloud * m * 3;
+    for (int j = tid; j < m; j += MT_TPB) {
+      const int k = idx[j];
+      out[3 * j] = xyz[3 * k]; out[3 * j + 1] = xyz[3 * k + 1]; out[3 * j + 2] = xyz[3 * k + 2];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ points, const int* __restrict__ idx,
                                                      int c, int n, int m, float* __restrict__ out) {
   const int i = blockIdx.z, l = blockIdx.y;
@@ -564,7 +836,7 @@ using namespace dusty;
 using namespace dusty::fps;
 
 static size_t fps_comp_bytes(int b, int n) { return align_up((size_t)b * 4 * ((n + 127) / 128 * 128) * sizeof(float), 256); }
-static size_t fps_temp_bytes(int b, int n) { return n > REG_CAP ? align_up((size_t)b * ((n + 3) & ~3) * sizeof(float), 256) : 0; }
+static size_t fps_temp_bytes(int b, int n) { return align_up((size_t)b * ((n + 127) / 128 * 128) * sizeof(float), 256); }
 
 extern "C" size_t dusty_fps_workspace_bytes(int b, int n, int m) {
   (void)m;
@@ -585,18 +857,25 @@ extern "C" int dusty_fps(const float* xyz, int b, int n, int m, int32_t* idx, fl
   float* comp = static_cast<float*>(workspace);
   float* temp = reinterpret_cast<float*>(static_cast<char*>(workspace) + fps_comp_bytes(b, n));
   static bool configured[kMaxDevices] = {};
-  static bool force_flat = false;
+  static bool force_flat = false, force_single = false, force_multi = false;
   const int dev = current_device();
   if (!configured[dev]) {
     DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DUSTY_CUDA(cudaFuncSetAttribute(fps_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
-    const char* env = getenv("DUSTY_FPS_FLAT");       // A/B switch for profiling; both kernels give the same indices
-    force_flat = env && env[0] == '1';
+    DUSTY_CUDA(cudaFuncSetAttribute(fps_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
+    const char* env = getenv("DUSTY_FPS_ALGO");       // A/B switch for profiling: flat | single | multi; same indices from all
+    force_flat = env && env[0] == 'f';
+    force_single = env && env[0] == 's';
+    force_multi = env && env[0] == 'm';
     configured[dev] = true;
   }
+  // more clouds than SMs: four clouds per SM hide each other's latency chain (throughput variant);
+  // otherwise one cloud per SM with everything on chip (latency variant)
+  const bool multi = force_multi || (!force_single && b > kNumSMs);
   if (n > REG_CAP) fps_flat_kernel<false><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
   else if (force_flat) fps_flat_kernel<true><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
+  else if (multi) fps_multi_kernel<<<b, MT_TPB, MT_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
   else fps_pruned_kernel<<<b, TPB, PR_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp);
   DUSTY_AFTER_LAUNCH("fps kernel");
   return 0;
