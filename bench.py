@@ -134,14 +134,19 @@ def make_lidar(device):
     return LiDAR(H, W, 0.9, 120.0, angle=synthetic_hdl64e_angles()).to(device)
 
 
-def make_clouds(n, seed, head, lidar, device):
+def make_clouds(n, seed, head, lidar, device, kind=1, full_resolution=False):
+    """n clouds through our head + projection (+ FPS unless full_resolution: then the un-sampled
+    (H*W,3) clouds with dropped pixels at the origin, configs[4]'s shape)."""
     from dusty_gan_b200 import pipeline
     out = []
-    for i in range(0, n, 250):
-        b = min(250, n - i)
-        depth, conf = backbone_like(b, 1, seed * 1000 + i, device)
-        pts, _ = pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, N_POINTS, tol=0.0)
-        out.append(pts)
+    step = 100 if full_resolution else 500
+    for i in range(0, n, step):
+        b = min(step, n - i)
+        depth, conf = backbone_like(b, kind, seed * 1000 + i, device)
+        if full_resolution:
+            out.append(pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"])
+        else:
+            out.append(pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, N_POINTS, tol=0.0)[0])
     return torch.cat(out).contiguous()
 
 
@@ -312,6 +317,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clouds", type=int, default=N_CLOUDS, help="clouds per set (default = configs[2])")
     ap.add_argument("--skip-extras", action="store_true", help="headline only (no stages / cpu baseline)")
+    ap.add_argument("--dusty", type=int, default=1, choices=[1, 2], help="head that makes the clouds (configs[3] uses DUSty-II)")
+    ap.add_argument("--full-resolution", action="store_true", help="configs[4]: un-sampled 64x512 clouds (32768 points each)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -330,10 +337,11 @@ def main():
     from dusty_gan_b200.utils.metrics import cov_mmd_1nna as M
     hbm_gbs, sm_max_mhz, peak_src = peaks()
     N = args.clouds
-    lidar = make_lidar(device); head = make_head(1, device)
+    lidar = make_lidar(device); head = make_head(args.dusty, device)
+    P = H * W if args.full_resolution else N_POINTS
     t0 = time.perf_counter()
-    ref = make_clouds(N, 2, head, lidar, device)
-    gen = make_clouds(N, 1, head, lidar, device)
+    ref = make_clouds(N, 2, head, lidar, device, args.dusty, args.full_resolution)
+    gen = make_clouds(N, 1, head, lidar, device, args.dusty, args.full_resolution)
     torch.cuda.synchronize()
     log(f"[rank {rank}] inputs ready in {time.perf_counter() - t0:.1f}s: 2 x {tuple(ref.shape)}")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
@@ -400,7 +408,7 @@ def main():
     value = entries / (ms_per_step * 1e-3)
     e2e_value = entries / (e2e_ms / args.steps * 1e-3)
     # roofline of the dominant kernel (chamfer nn_kernel): FP32 FFMA
-    flops_per_entry = 12.0 * N_POINTS * N_POINTS
+    flops_per_entry = 12.0 * P * P
     alg_flops = entries * flops_per_entry / world                           # per launch, this GPU's share
     exe_entries = (2 * N) * (2 * N + 1) / 2                                 # stacked upper triangle incl. diagonal
     exe_flops = exe_entries * flops_per_entry / world
@@ -415,7 +423,7 @@ def main():
     probe_ms = min(time_events(probe, 5, 2))
     peak_probe = flops.value / (probe_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "fp32_ffma", "kernel": "dusty::chamfer::nn_kernel<8,true>",
+        "bound": "fp32_ffma", "kernel": "dusty::chamfer::nn_kernel<8,true>", "points_per_cloud": P,
         "achieved": alg_flops / (kern_ms * 1e-3) / 1e12, "peak": peak_nominal, "unit": "TFLOP/s",
         "frac": alg_flops / (kern_ms * 1e-3) / 1e12 / peak_nominal,
         "executed": exe_flops / (kern_ms * 1e-3) / 1e12, "executed_frac": exe_flops / (kern_ms * 1e-3) / 1e12 / peak_nominal,
@@ -431,7 +439,10 @@ def main():
         "metric": "chamfer_pairs_per_s", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[2]: {N} vs {N} clouds x {N_POINTS} FPS points, full MMD/COV/1-NNA via Chamfer",
+        "config": {"workload": (f"configs[2]: {N} vs {N} clouds x {N_POINTS} FPS points, full MMD/COV/1-NNA via Chamfer"
+                                if (N == N_CLOUDS and args.dusty == 1 and not args.full_resolution) else
+                                f"{N} vs {N} clouds x {P} points (DUSty-{'II' if args.dusty == 2 else 'I'} head"
+                                f"{', un-sampled' if args.full_resolution else ', FPS'}), full MMD/COV/1-NNA via Chamfer"),
                    "entries_per_step": entries, "clouds_from": "synthetic 64x512 range images -> head+projection+FPS kernels",
                    "parallelism": f"row-sharded x{world}, one all-gather" if world > 1 else "single GPU",
                    "l2": "256 MB buffer written between timed steps (inputs 49 MB + 64 MB scan copies < 126 MB L2)"},

@@ -11,5 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:nn_kernel -s 1 -c 1 -f -o gpurun_out/prof_chamfer_${R} \
     python bench.py --steps 1 --warmup 1 --skip-extras > gpurun_out/prof_chamfer_${R}.log 2>&1
 # 3. head + projection and FPS kernels
-ncu --set full --clock-control none --import-source on -k regex:"head_project_kernel|fps_kernel" -s 2 -c 2 -f \
+ncu --set full --clock-control none --import-source on -k regex:"head_project_kernel|fps_" -s 2 -c 2 -f \
     -o gpurun_out/prof_stages_${R} python profiles/stage_driver.py > gpurun_out/prof_stages_${R}.log 2>&1
