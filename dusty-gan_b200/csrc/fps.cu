@@ -417,8 +417,10 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
         l0 = warp_min_f(l0); l1 = warp_min_f(l1); l2 = warp_min_f(l2);
         h0 = warp_max_f(h0); h1 = warp_max_f(h1); h2 = warp_max_f(h2);
         if (lane == 0) {
-          blo[b] = make_float4(l0, l1, l2, 0.f); bhi[b] = make_float4(h0, h1, h2, 0.f);
-          rec[b] = BucketRec{1e10f, e0};      // every bucket is touched in iteration 1 (LB < 1e10) before this is read
+          // records of one warp are contiguous (slot-major per warp): the per-lane reads below are conflict-free
+          const int sidx = warp * GROUPS_MAX + i;
+          blo[sidx] = make_float4(l0, l1, l2, 0.f); bhi[sidx] = make_float4(h0, h1, h2, 0.f);
+          rec[sidx] = BucketRec{1e10f, e0};   // every bucket is touched in iteration 1 (LB < 1e10) before this is read
         }
       }
     }
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
       // (a) one bucket per lane: can the new centre lower any distance in it?
       const int btest = lane * NW + warp;                       // slot `lane` of this warp
       const bool bvalid = lane < GROUPS_MAX && btest < nb;
-      const int bsafe = bvalid ? btest : warp;                  // bucket `warp` (slot 0) always exists when it matters
+      const int bsafe = warp * GROUPS_MAX + (bvalid ? lane : 0);   // storage index of that bucket's box/record
       bool upd;
       {
         const float4 l4 = blo[bsafe], h4 = bhi[bsafe];
@@ -479,9 +481,9 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
             }
           }
           const unsigned kmin = __reduce_min_sync(0xffffffffu, lk);
-          if (lk == kmin && cm != 0u) rec[i * NW + warp] = BucketRec{__uint_as_float(vmax), ebest};
+          if (lk == kmin && cm != 0u) rec[warp * GROUPS_MAX + i] = BucketRec{__uint_as_float(vmax), ebest};
         } else if (cm != 0u) {
-          rec[i * NW + warp] = BucketRec{__uint_as_float(vmax), ebest};
+          rec[warp * GROUPS_MAX + i] = BucketRec{__uint_as_float(vmax), ebest};
         }
       };
       for (unsigned todo = need; todo != 0u; todo &= todo - 1u) {          // warp-uniform
@@ -694,8 +696,9 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
       l0 = warp_min_f(l0); l1 = warp_min_f(l1); l2 = warp_min_f(l2);
       h0 = warp_max_f(h0); h1 = warp_max_f(h1); h2 = warp_max_f(h2);
       if (lane == 0) {
-        blo[b] = make_float4(l0, l1, l2, 0.f); bhi[b] = make_float4(h0, h1, h2, 0.f);
-        rec[b] = MtRec{1e10f, e0, X[0], Y[0], Z[0], 0.f, 0.f, 0.f};   // replaced in iteration 1 (LB < 1e10 everywhere)
+        const int sidx = warp * 32 + b / MT_NW;      // records of one warp are contiguous: conflict-free per-lane reads
+        blo[sidx] = make_float4(l0, l1, l2, 0.f); bhi[sidx] = make_float4(h0, h1, h2, 0.f);
+        rec[sidx] = MtRec{1e10f, e0, X[0], Y[0], Z[0], 0.f, 0.f, 0.f};   // replaced in iteration 1 (LB < 1e10 everywhere)
       }
     }
     __syncthreads();
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
       // (a) lane l tests the warp's slot l
       const int btest = lane * MT_NW + warp;
       const bool bvalid = btest < nb;
-      const int bsafe = bvalid ? btest : 0;
+      const int bsafe = warp * 32 + (bvalid ? lane : 0);        // storage index of that bucket's box/record
       bool upd;
       {
         const float4 l4 = blo[bsafe], h4 = bhi[bsafe];
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
           const float wx = qb == 0 ? px.x : qb == 1 ? px.y : qb == 2 ? px.z : px.w;
           const float wy = qb == 0 ? py.x : qb == 1 ? py.y : qb == 2 ? py.z : py.w;
           const float wz = qb == 0 ? pz.x : qb == 1 ? pz.y : qb == 2 ? pz.z : pz.w;
-          rec[b] = MtRec{__uint_as_float(vmax), e0 + qb, wx, wy, wz, 0.f, 0.f, 0.f};
+          rec[warp * 32 + (__ffs(todo) - 1)] = MtRec{__uint_as_float(vmax), e0 + qb, wx, wy, wz, 0.f, 0.f, 0.f};
         }
       }
       __syncwarp();
