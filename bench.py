@@ -203,7 +203,7 @@ def bench_stages(device, hbm_gbs, peak_src, flush):
             "note": f"configs[1]: batch {HEAD_BATCH} of {H}x{W}; {reps} launches replayed as a CUDA graph, outputs preallocated; "
                     "working set per launch exceeds L2"}
     head = make_head(1, device)
-    n_fps = 592                                   # four clouds per SM: the throughput variant of the FPS kernel
+    n_fps = 888                                   # six clouds per SM: the throughput variant of the FPS kernel
     depth, conf = backbone_like(n_fps, 1, 12, device)
     pts = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"]
     mag = (pts.double() ** 2).sum(-1)

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 // Pruned kernel, throughput variant: same algorithm, but nothing large is on chip. Coordinates and
 // running distances stay in the L2-resident workspace (a pruned iteration touches ~6 % of them),
-// only the bucket boxes/records live in shared memory, so four clouds share one SM and overlap
+// only the bucket boxes/records live in shared memory, so up to six clouds share one SM and overlap
 // each other's per-iteration latency chain (prune test -> update -> REDUX -> barrier -> REDUX).
 // Records carry the winner's coordinates so the next centre never costs an L2 round trip.
 // ------------------------------------------------------------------------------------------------
@@ -555,14 +555,14 @@ constexpr int MT_TPB = 256;
 constexpr int MT_NW = MT_TPB / 32;                 // 8 warps; lane l of a warp tests the warp's slot l
 constexpr int MT_BUCKETS = MT_NW * 32;             // 256 buckets = 32768 points
 constexpr int MT_ELIST = 1536;
-constexpr int MT_SMEM_BYTES = MT_BUCKETS * (16 + 16 + 32) + MT_ELIST * 4;   // boxes + records + winner list = 22 KB
+constexpr int MT_SMEM_BYTES = MT_BUCKETS * (16 + 16 + 32 + 4) + MT_ELIST * 4;   // boxes + records + max distances + winner list = 23 KB
 static_assert(MT_SMEM_BYTES >= CELLS * 4, "the cell counters alias the box/record region");
 
 struct MtRec { float maxT; int e; float x, y, z; float pad0, pad1, pad2; };   // 32 B
 struct MtWin { unsigned val; int e; float x, y, z; };
 
 // comp layout per cloud: x[n128] y[n128] z[n128] oidx[n128]; dist_all: t[n128]
-__global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __restrict__ xyz_all, int n, int m,
+__global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __restrict__ xyz_all, int n, int m,
                                                               int* __restrict__ idx_all, float* __restrict__ out_all,
                                                               float* __restrict__ comp_all, float* __restrict__ dist_all) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -570,7 +570,8 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
   float4* const blo = reinterpret_cast<float4*>(smraw);
   float4* const bhi = blo + MT_BUCKETS;
   MtRec* const rec = reinterpret_cast<MtRec*>(bhi + MT_BUCKETS);
-  int* const elist = reinterpret_cast<int*>(rec + MT_BUCKETS);
+  float* const bmax = reinterpret_cast<float*>(rec + MT_BUCKETS);   // rec[].maxT again, densely: the per-lane compare key
+  int* const elist = reinterpret_cast<int*>(bmax + MT_BUCKETS);
   __shared__ float red[MT_NW][8];
   __shared__ int wsum[MT_NW];
   __shared__ MtWin slots[2][MT_NW];
@@ -699,6 +700,7 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
         const int sidx = warp * 32 + b / MT_NW;      // records of one warp are contiguous: conflict-free per-lane reads
         blo[sidx] = make_float4(l0, l1, l2, 0.f); bhi[sidx] = make_float4(h0, h1, h2, 0.f);
         rec[sidx] = MtRec{1e10f, e0, X[0], Y[0], Z[0], 0.f, 0.f, 0.f};   // replaced in iteration 1 (LB < 1e10 everywhere)
+        bmax[sidx] = 1e10f;
       }
     }
     __syncthreads();
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
       bool upd;
       {
         const float4 l4 = blo[bsafe], h4 = bhi[bsafe];
-        const float mt = rec[bsafe].maxT;
+        const float mt = bmax[bsafe];
         const float gx = max3(0.0f, l4.x - ccx, ccx - h4.x);
         const float gy = max3(0.0f, l4.y - ccy, ccy - h4.y);
         const float gz = max3(0.0f, l4.z - ccz, ccz - h4.z);
@@ -767,23 +769,23 @@ __global__ void __launch_bounds__(MT_TPB, 4) fps_multi_kernel(const float* __res
           const float wy = qb == 0 ? py.x : qb == 1 ? py.y : qb == 2 ? py.z : py.w;
           const float wz = qb == 0 ? pz.x : qb == 1 ? pz.y : qb == 2 ? pz.z : pz.w;
           rec[warp * 32 + (__ffs(todo) - 1)] = MtRec{__uint_as_float(vmax), e0 + qb, wx, wy, wz, 0.f, 0.f, 0.f};
+          bmax[warp * 32 + (__ffs(todo) - 1)] = __uint_as_float(vmax);
         }
       }
       __syncwarp();
 
       // (c) best bucket of this warp, (d) best warp of the block
-      const MtRec rr = rec[bsafe];
-      const unsigned vb = bvalid ? __float_as_uint(rr.maxT) : 0u;
+      const unsigned vb = bvalid ? __float_as_uint(bmax[bsafe]) : 0u;
       const unsigned V = __reduce_max_sync(0xffffffffu, vb);
       unsigned cand = __ballot_sync(0xffffffffu, bvalid && vb == V);
       if ((cand & (cand - 1)) != 0u) {
-        const unsigned key = (bvalid && vb == V) ? tiekey(co[rr.e]) : 0xffffffffu;
+        const unsigned key = (bvalid && vb == V) ? tiekey(co[rec[bsafe].e]) : 0xffffffffu;
         const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
         cand = __ballot_sync(0xffffffffu, key == kmin);
       }
       const int par = j & 1;
       if (cand == 0u) { if (lane == 0) slots[par][warp] = MtWin{0u, -1, 0.f, 0.f, 0.f}; }
-      else if (lane == __ffs(cand) - 1) slots[par][warp] = MtWin{V, rr.e, rr.x, rr.y, rr.z};
+      else if (lane == __ffs(cand) - 1) { const MtRec rr = rec[bsafe]; slots[par][warp] = MtWin{V, rr.e, rr.x, rr.y, rr.z}; }
       __syncthreads();
       const MtWin s2 = slots[par][lane & (MT_NW - 1)];
       const bool sv = lane < MT_NW && s2.e >= 0;
