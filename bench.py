@@ -142,7 +142,7 @@ def make_clouds(n, seed, head, lidar, device, kind=1, full_resolution=False):
     step = 100 if full_resolution else 500
     for i in range(0, n, step):
         b = min(step, n - i)
-        depth, conf = backbone_like(b, kind, seed * 1000 + i, device)
+        depth, conf = backbone_like(b, kind, seed * 1000003 + i, device)      # distinct streams for any n
         if full_resolution:
             out.append(pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"])
         else:

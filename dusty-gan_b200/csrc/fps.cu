@@ -17,8 +17,8 @@
 //
 // fps_pruned_kernel (n <= 32768, the path every config takes)
 //   prologue  eligible points are counting-sorted by a 4096-cell grid (x,y Morton-interleaved, z low
-//             bits) into a SoA copy -- first SMEM_CAP points in shared memory, the rest in the
-//             L2-resident workspace -- so that the 128 points owned by one (warp, slot) pair form a
+//             bits) into a SoA copy in the L2-resident workspace, whose first 17 792 points are then
+//             staged into shared memory by 1-D TMA bulk copies, so that the 128 points owned by one (warp, slot) pair form a
 //             spatially tight *bucket*; each bucket keeps its bounding box and (max distance, tie
 //             key, position, original index) of its current best point in shared memory;
 //   loop      running distances never leave registers (64 per thread). Per iteration a lane tests
@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
   __shared__ float red[NW][8];
   __shared__ int wsum[NW];
   __shared__ WinRec slots[2][NW];
+  __shared__ uint64_t stage_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long cloud = blockIdx.x;
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
   float* const cz = cy + n128;
   int* const co = reinterpret_cast<int*>(cz + n128);
   const float inf = __int_as_float(0x7f800000);
+  if (tid == 0) { mbar_init(&stage_bar, 1); mbar_fence_init(); }
 
   // tie key of the reference: (bitreverse_L(k mod T), k div T) as one integer
   int L = 0;
@@ -368,17 +370,26 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
       if (!((double)mag <= 1e-3)) {
         const int e = atomicAdd(&cells[cell_of(x, y, z)], 1);
         cx[e] = x; cy[e] = y; cz[e] = z; co[e] = k;
-        if (e < PR_CAP) { sx[e] = x; sy[e] = y; sz[e] = z; }
       }
     }
     const int E_pad = (E + BUCKET - 1) / BUCKET * BUCKET;
     if (tid < E_pad - E) {               // fill the last bucket; padding never wins (distance -1) nor widens a box
       const int e = E + tid;
       cx[e] = 0.f; cy[e] = 0.f; cz[e] = 0.f; co[e] = 0;
-      if (e < PR_CAP) { sx[e] = 0.f; sy[e] = 0.f; sz[e] = 0.f; }
     }
+    // The sorted cloud is staged into shared memory by three 1-D TMA bulk copies (UBLKCP) from the
+    // L2-resident workspace: make the generic-proxy writes above visible to the async proxy first.
     __threadfence_block();
+    asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();                     // cell counters are dead from here on: region A becomes boxes + records
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)min(E_pad, PR_CAP) * 4u;
+      mbar_expect_tx(&stage_bar, 3u * bytes);
+      bulk_g2s(sx, cx, bytes, &stage_bar);
+      bulk_g2s(sy, cy, bytes, &stage_bar);
+      bulk_g2s(sz, cz, bytes, &stage_bar);
+    }
+    mbar_wait(&stage_bar, 0u);
 
     const int nb = E_pad / BUCKET;       // buckets in use; bucket b = slot * NW + warp
 
