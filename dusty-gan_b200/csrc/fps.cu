@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(TPB, 1) fps_pruned_kernel(const float* __restr
         upd = bvalid && lb < mt;
       }
       const unsigned need = __ballot_sync(0xffffffffu, upd);
+      __syncwarp();      // orders the record reads above before the record writes below (other lanes)
 
       // (b) update the buckets that may change and re-elect their best point. Distances live in
       //     registers, so the slot is selected through a jump table instead of 16 predicated blocks.
@@ -733,6 +734,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
         upd = bvalid && lb < mt;
       }
       const unsigned need = __ballot_sync(0xffffffffu, upd);
+      __syncwarp();      // orders the record reads above before the record writes below (other lanes)
 
       // (b) update the buckets that may change
       const f32x2 c2x = pack2(ccx, ccx), c2y = pack2(ccy, ccy), c2z = pack2(ccz, ccz);
