@@ -219,6 +219,41 @@ def bench_stages(device, hbm_gbs, peak_src, flush):
         pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, N_POINTS, tol=0.0)
     ms = time_events(img2cloud, 3, 1)
     res["range_image_to_fps_clouds_per_s"] = n_fps / (statistics.median(ms) * 1e-3)
+    res.update(bench_real_side(device, hbm_gbs, peak_src))
+    return res
+
+
+def bench_real_side(device, hbm_gbs, peak_src):
+    """raw (64,2048,4) scans -> (inv, mask, points) in one kernel (the reference: numpy per
+    scan on DataLoader workers + ~12 ATen kernels per batch), at the evaluation's 64x512 and at full width."""
+    from dusty_gan_b200.datasets import preprocess_scans
+    n = 256
+    g = torch.Generator(device=device).manual_seed(21)
+    elev = torch.deg2rad(torch.linspace(2.0, -24.8, H, device=device))[:, None]
+    azim = torch.linspace(np.pi, -np.pi, 2049, device=device)[:-1][None, :]
+    r = (25 + 12 * torch.randn(n, H, 2048, generator=g, device=device)).abs() + 0.3
+    r = r * (torch.rand(n, H, 2048, generator=g, device=device) > 0.25)          # empty pixels
+    scans = torch.stack([r * torch.cos(elev) * torch.cos(azim), r * torch.cos(elev) * torch.sin(azim),
+                         r * torch.sin(elev), torch.rand(n, H, 2048, generator=g, device=device)], dim=-1).contiguous()
+    del r
+    res = {}
+    for w_out in (W, 2048):
+        bufs = preprocess_scans(scans, (H, w_out), 0.9, 120.0, -1)
+        reps = 10
+
+        def run():
+            for _ in range(reps):           # back to back: one launch alone is latency dominated
+                preprocess_scans(scans, (H, w_out), 0.9, 120.0, -1, buffers=bufs)
+        ms = statistics.median(time_events(run, 5, 2)) / reps
+        # algorithmic bytes per output pixel: one (x,y,z,reflectance) source point in, inv + mask + xyz out
+        bytes_alg = n * H * w_out * (16 + 4 + 4 + 12)
+        res[f"scan_preprocess_w{w_out}"] = {
+            "scans_per_s": n / (ms * 1e-3), "ms": ms, "scans": n,
+            "roofline": {"bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": hbm_gbs, "unit": "GB/s",
+                         "frac": bytes_alg / ms / 1e6 / hbm_gbs, "peak_source": peak_src, "algorithmic_bytes": bytes_alg},
+            "note": f"{n} scans of 64x2048x4 -> 64x{w_out} (nearest), {reps} back-to-back API calls, outputs preallocated, "
+                    f"working set {n * 2} MB in > L2; "
+                    + ("every 4th source point is read: sectors are half used" if w_out != 2048 else "every source point is read")}
     return res
 
 

@@ -31,6 +31,13 @@ class HeadParams(C.Structure):
                 ("points_layout", C.c_int32)]
 
 
+class ScanParams(C.Structure):
+    _fields_ = [("b", C.c_int32), ("hs", C.c_int32), ("ws", C.c_int32), ("channels", C.c_int32),
+                ("h", C.c_int32), ("w", C.c_int32), ("scale_h", C.c_float), ("scale_w", C.c_float),
+                ("min_depth", C.c_float), ("max_depth", C.c_float), ("range", C.c_float),
+                ("disp_lo", C.c_float), ("inv_disp_range", C.c_float), ("drop_const", C.c_float)]
+
+
 NOISE_NONE, NOISE_LOGISTIC, NOISE_UNIFORM = 0, 1, 2
 MATRIX_SYMMETRIC, MATRIX_MIRROR, MATRIX_COMPACT_ROWS, MATRIX_PREPARED = 1, 2, 4, 8
 
@@ -68,6 +75,8 @@ SIGNATURES = {
     "dusty_head_project": (C.c_int, [C.POINTER(HeadParams), c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                      c_float_p, c_int_p, c_int_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dusty_inv_to_xyz": (C.c_int, [C.POINTER(HeadParams), c_float_p, c_float_p, c_float_p, C.c_void_p]),
+    "dusty_scan_preprocess": (C.c_int, [C.POINTER(ScanParams), c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                        c_float_p, C.c_void_p]),
     "dusty_probe_fp32_peak": (C.c_int, [C.c_int, c_float_p, C.POINTER(C.c_double), C.c_void_p]),
 }
 

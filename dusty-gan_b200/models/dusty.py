@@ -102,8 +102,9 @@ class GumbelSigmoid(nn.Module):
         self.fixed_noise = None
 
     def _inv_tau(self):
-        # ATen's CUDA division by a Python scalar multiplies by the f32 reciprocal (trap T2)
-        return np.float32(1.0) / np.float32(self.tau)
+        # ATen's CUDA division by a Python scalar multiplies by the reciprocal, formed in double and
+        # rounded to f32 once (trap T2; torch 2.11 div_true_kernel_cuda)
+        return np.float32(1.0 / self.tau)
 
     def _logistic_from_uniform(self, u1, u2):
         out = torch.empty_like(u1)
@@ -132,15 +133,16 @@ class GumbelSigmoid(nn.Module):
 def _projection_fields(params, lidar, tol):
     """Fill the projection scalars exactly as the reference's element-wise kernels receive them
     (reference utils/lidar.py:23-29,38-47,61-68): Python-double arithmetic on the config values,
-    then one cast to f32; divisions by a Python scalar become f32 reciprocal multiplies on CUDA."""
+    then one cast to f32; a division by a Python scalar is a multiply by f32(1/scalar), the reciprocal
+    taken in double (torch 2.11 div_true_kernel_cuda)."""
     f32 = np.float32
     params.tol = f32(tol)
     params.disp_scale = f32(1 / lidar.min_depth - 1 / lidar.max_depth)
     params.disp_shift = f32(1 / lidar.max_depth)
     params.min_depth = f32(lidar.min_depth)
     params.range = f32(lidar.max_depth - lidar.min_depth)
-    params.inv_range = f32(1.0) / f32(lidar.max_depth - lidar.min_depth)
-    params.inv_max_depth = f32(1.0) / f32(lidar.max_depth)
+    params.inv_range = f32(1.0 / (lidar.max_depth - lidar.min_depth))
+    params.inv_max_depth = f32(1.0 / lidar.max_depth)
 
 
 def _drop_value(module):

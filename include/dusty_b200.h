@@ -30,6 +30,10 @@
  *                                DUSty1.maskout, DUSty2.maskout) fused with utils/__init__.py:76-79
  *                                (tanh_to_sigmoid + clamp) and utils/lidar.py:38-68 (inv_to_xyz)
  *   dusty_inv_to_xyz             utils/lidar.py:61-68     (Coordinate.inv_to_xyz alone)
+ *   dusty_scan_preprocess        datasets/kitti.py:54-78 (KITTIOdometry.preprocess + transform's nearest
+ *                                resize) fused with evaluate_synthesis.py:49-57 (preprocess_reals:
+ *                                utils/lidar.py:31-36 invert_depth, utils/__init__.py:70-73 sigmoid_to_tanh,
+ *                                mask blend, flatten/transpose): the real-data side of the path
  */
 #ifndef DUSTY_B200_H_
 #define DUSTY_B200_H_
@@ -193,7 +197,7 @@ typedef struct dusty_head_params {
   int32_t conf_channels;    /* 1 (DUSty-I) or 2 (DUSty-II: channel 0 pixel gate, channel 1 image gate) */
   dusty_gate gate_pixel;
   dusty_gate gate_image;    /* ignored when conf_channels == 1 */
-  float inv_tau;            /* 1/tau as the reference's kernel forms it (f32 reciprocal) */
+  float inv_tau;            /* f32(1.0/tau): ATen CUDA forms x/scalar as x * f32(1/double(scalar)) */
   float threshold;          /* mask_soft > threshold */
   float eps;                /* 1e-10 */
   float drop_const;         /* generator-side drop value, -1 */
@@ -202,9 +206,9 @@ typedef struct dusty_head_params {
   float disp_scale;         /* f32(1/min_depth - 1/max_depth) */
   float disp_shift;         /* f32(1/max_depth) */
   float min_depth;          /* f32(min_depth) */
-  float inv_range;          /* 1.0f / f32(max_depth - min_depth) */
+  float inv_range;          /* f32(1.0 / (max_depth - min_depth)), reciprocal in double */
   float range;              /* f32(max_depth - min_depth) */
-  float inv_max_depth;      /* 1.0f / f32(max_depth) */
+  float inv_max_depth;      /* f32(1.0 / max_depth) */
   int32_t points_layout;    /* 0: xyz planar (b,3,h,w) like inv_to_xyz; 1: interleaved (b,h*w,3) */
 } dusty_head_params;
 
@@ -232,6 +236,36 @@ DUSTY_API int dusty_head_project(const dusty_head_params* p, const float* depth,
 /* Projection only: inv (b,1,h,w) in [0,1] (already tanh_to_sigmoid'ed and clamped) -> xyz. */
 DUSTY_API int dusty_inv_to_xyz(const dusty_head_params* p, const float* inv, const float* trig,
                      float* out_points, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Real-data side: organised LiDAR scans -> range images + clouds (the reference set of the evaluation)
+ * -------------------------------------------------------------------------------------------- */
+
+typedef struct dusty_scan_params {
+  int32_t b, hs, ws;        /* scans (b,hs,ws,channels) f32 as process_kitti.py stores them: (64,2048,4) */
+  int32_t channels;         /* >= 3; xyz are channels 0..2 (channel 3 = reflectance, unused on this path) */
+  int32_t h, w;             /* output range-image shape; w a multiple of 4 */
+  float scale_h, scale_w;   /* f32(hs)/h, f32(ws)/w: source index = min((int)floorf(dst*scale), size-1),
+                               torch's nearest interpolation (torchvision TF.resize(..., NEAREST)) */
+  float min_depth;          /* f32(min_depth): mask = r > 0 && r > min_depth && r < max_depth */
+  float max_depth;          /* f32(max_depth); also xyz /= max_depth (true division) */
+  float range;              /* f32(max_depth - min_depth): depth = (r - min_depth) / range (true division) */
+  /* invert_depth + sigmoid_to_tanh as ATen's CUDA element-wise kernels round them */
+  float disp_lo;            /* f32(1/max_depth) */
+  float inv_disp_range;     /* f32(1.0 / (1/min_depth - 1/max_depth)) */
+  float drop_const;         /* generator-side drop value (-1): inv = mask*inv + (1-mask)*drop_const */
+} dusty_scan_params;
+
+/* One pass over a batch of scans. Outputs (any of out_depth / out_xyz may be NULL):
+ *   out_depth  (b,1,h,w)  normalised range in [0,1], 0 where masked        (dataset "depth")
+ *   out_mask   (b,1,h,w)  1.0 / 0.0                                         (dataset "mask", .float())
+ *   out_inv    (b,1,h,w)  tanh-space inverse depth, drop_const where masked (preprocess_reals "inv")
+ *   out_points (b,h*w,3)  unit-space xyz, interleaved (what FPS consumes); origin where masked
+ *   out_xyz    (b,3,h,w)  the same, planar                                  (dataset "xyz")
+ * scans must be 4-byte aligned (16-byte when channels == 4 for the vector path, checked at run
+ * time); outputs 16-byte aligned. */
+DUSTY_API int dusty_scan_preprocess(const dusty_scan_params* p, const float* scans, float* out_depth,
+                          float* out_mask, float* out_inv, float* out_points, float* out_xyz, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * Measurement helper (bench.py only): sustained dependent-free FFMA rate, for the FP32 roofline.

@@ -19,7 +19,7 @@ def test_header_declares_the_documented_entry_points():
     syms = declared_symbols()
     for must in ("dusty_chamfer_forward", "dusty_chamfer_matrix", "dusty_fps", "dusty_gather_points",
                  "dusty_head_project", "dusty_inv_to_xyz", "dusty_gumbel_sigmoid", "dusty_logistic_noise",
-                 "dusty_cov_mmd_1nna_finalize", "dusty_chamfer_backward"):
+                 "dusty_cov_mmd_1nna_finalize", "dusty_chamfer_backward", "dusty_scan_preprocess"):
         assert must in syms
 
 
@@ -66,6 +66,10 @@ def test_argument_errors_are_reported_not_printed():
     with pytest.raises(RuntimeError, match="code -1"):
         _lib.check(rc, "dusty_chamfer_forward")
     assert lib.dusty_fps(None, 1, 0, 4, None, None, None, 0, None) == -1
+    p = _lib.ScanParams()
+    p.b, p.hs, p.ws, p.channels, p.h, p.w = 1, 64, 2048, 2, 64, 512
+    assert lib.dusty_scan_preprocess(p, None, None, None, None, None, None, None) == -1
+    assert b"bad shape" in lib.dusty_last_error_string()
 
 
 def test_ops_refuse_cpu_tensors():

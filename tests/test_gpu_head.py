@@ -103,6 +103,27 @@ def test_inv_to_xyz_bit_exact_and_tolerances(golden):
         assert np.array_equal(xyz.cpu().numpy() == 0, g[key] == 0)
 
 
+@pytest.mark.parametrize("min_depth,max_depth,tau", [(1.72, 67.2, 1.19), (2.95, 144.9, 0.7), (0.53, 129.9, 1.0)])
+def test_other_depth_limits_and_temperatures_bit_exact(min_depth, max_depth, tau):
+    """Limits/temperatures for which f32(1/double(s)) != 1.0f/f32(s): ATen's CUDA kernels divide by a
+    Python scalar by multiplying with the former (torch 2.11 div_true_kernel_cuda)."""
+    from dusty_gan_b200.models.dusty import DUSty1
+    from dusty_gan_b200.utils.lidar import LiDAR, synthetic_hdl64e_angles
+    from dusty_gan_b200 import pipeline
+    B, H, W = 3, 16, 64
+    depth, conf, u1, u2 = head_inputs(B, 1, H, W, 77, "cuda")
+    head = DUSty1(torch.nn.Identity(), tau=tau).cuda().eval()
+    head.gumbel.fixed_noise = head.gumbel._logistic_from_uniform(u1, u2)
+    lidar = LiDAR(H, W, min_depth, max_depth, angle=synthetic_hdl64e_angles()).cuda()
+    mask, dout = hp.maskout_dusty1(depth, conf, hp.logistic_noise(u1, u2), tau=tau)
+    fused = pipeline.maskout_and_project(head, {"depth": depth.clone(), "confidence": conf.clone()}, lidar, tol=0.0)
+    assert_bit_equal(fused["mask"], mask, "mask")
+    assert_bit_equal(fused["depth"], dout, "depth")
+    assert_bit_equal(fused["points"], hp.project_2d_to_3d_dense(dout, lidar.angle, min_depth, max_depth, 0.0), "points")
+    inv = torch.rand(B, 1, H, W, device="cuda")
+    assert_bit_equal(lidar.inv_to_xyz(inv, 0.0), hp.inv_to_xyz(inv.clone(), lidar.angle, min_depth, max_depth, 0.0), "xyz")
+
+
 @pytest.mark.parametrize("name,kind", [("head_dusty1_eval.npz", 1), ("head_dusty2_eval.npz", 2)])
 def test_against_reference_module_golden(golden, name, kind):
     from dusty_gan_b200.models.dusty import DUSty1, DUSty2

@@ -182,3 +182,31 @@ def test_jsd_oracle_matches_reference(golden):
     assert cg.sum() == g["gen"].shape[0] * g["gen"].shape[1]
     assert oj.jsd_from_counts(cg, cr) == pytest.approx(float(g["jsd"]), rel=1e-5)
     assert oj.compute_jsd(g["gen"], g["ref"]) == pytest.approx(float(g["jsd"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(16, 64), (12, 96), (16, 256)])
+def test_real_data_oracle_matches_reference_dataset(golden, shape):
+    """oracle.real_data against the reference's KITTIOdometry.preprocess/transform, LiDAR.invert_depth and
+    sigmoid_to_tanh run on CPU (tests/golden/real_data.npz, oracle/gen_golden_real.py): bit-equal."""
+    from oracle import real_data as rd
+    g = golden("real_data.npz")
+    tag = f"_{shape[0]}x{shape[1]}"
+    items = [rd.dataset_item(s, shape) for s in g["scans"]]
+    raw = {k: torch.stack([it[k] for it in items]) for k in items[0]}
+    inv, mask, points = rd.preprocess_reals(raw)
+    for key, got in (("xyz", raw["xyz"]), ("depth", raw["depth"]), ("inv", inv), ("points", points)):
+        assert np.array_equal(got.numpy().view(np.int32), g[key + tag].view(np.int32)), key
+    assert np.array_equal(raw["mask"].numpy(), g["mask" + tag])
+    assert np.array_equal(mask.numpy() > 0, g["mask" + tag])
+    # the razor-edge returns planted by the generator (row 0 of scan 0, source columns 0,4,...,24)
+    if shape == (16, 256):
+        assert g["mask" + tag][0, 0, 0, [0, 4, 8, 12, 16, 20, 24]].tolist() == [False, True, False, True, False, False, False]
+
+
+def test_nearest_index_is_torchs():
+    from oracle import real_data as rd
+    import torch.nn.functional as F
+    for n_in, n_out in ((2048, 512), (2048, 2048), (256, 96), (100, 36), (64, 128), (7, 5)):
+        src = torch.arange(n_in, dtype=torch.float32)[None, None, None]
+        want = F.interpolate(src, size=(1, n_out), mode="nearest")[0, 0, 0].long().numpy()
+        assert np.array_equal(rd.nearest_index(n_out, n_in), want), (n_in, n_out)
