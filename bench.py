@@ -220,7 +220,46 @@ def bench_stages(device, hbm_gbs, peak_src, flush):
     ms = time_events(img2cloud, 3, 1)
     res["range_image_to_fps_clouds_per_s"] = n_fps / (statistics.median(ms) * 1e-3)
     res.update(bench_real_side(device, hbm_gbs, peak_src))
+    try:
+        stage_cpu_baselines(res, head, lidar, depth[:32], conf[:32], pts[:2])
+    except Exception as exc:        # the checker is optional for the measurement
+        res["cpu_baselines_error"] = repr(exc)[:200]
     return res
+
+
+def stage_cpu_baselines(res, head, lidar, depth, conf, pts):
+    """cpu_baseline leg of the stages: the reference's op chains on the host cores, bounded
+    samples. The head/projection/real-data chains are the reference's PyTorch/numpy ops (oracle restatement,
+    kind "port"); the reference has NO CPU FPS (fps/...cpp:96), so that line is the oracle's C replay."""
+    from oracle import head_projection as hp, native, real_data as rd
+    threads = torch.get_num_threads()
+    d, c = depth.cpu(), conf.cpu()
+    noise, angle = head.gumbel.fixed_noise.cpu(), lidar.angle.cpu()
+
+    def head_cpu():
+        mask, dout = hp.maskout_dusty1(d, c, noise)
+        return hp.project_2d_to_3d_dense(dout, angle, 0.9, 120.0, 0.0)
+    head_cpu()
+    t0 = time.perf_counter(); head_cpu(); dt = time.perf_counter() - t0
+    res["head_project_dusty1"]["cpu_baseline"] = {
+        "value": len(d) / dt, "unit": "images/s", "cores": threads, "kind": "port",
+        "sample": f"{len(d)} images of {H}x{W} through the reference's ATen op chain (models/dusty.py:45-91, "
+                  f"utils/lidar.py:38-68) on CPU, {threads} torch threads"}
+    p = pts.cpu().numpy()
+    t0 = time.perf_counter(); native.fps(p, N_POINTS); dt = time.perf_counter() - t0
+    res["fps"]["cpu_baseline"] = {
+        "value": len(p) / dt, "unit": "clouds/s", "cores": 1, "kind": "port",
+        "sample": f"{len(p)} clouds of {H * W} points -> {N_POINTS}: oracle's single-thread C replay of the reference "
+                  "CUDA kernel (the reference has no CPU FPS)"}
+    scans = rd.synthetic_scans(4, seed=1)
+    t0 = time.perf_counter()
+    items = [rd.dataset_item(x, (H, W)) for x in scans]
+    rd.preprocess_reals({k: torch.stack([it[k] for it in items]) for k in items[0]})
+    dt = time.perf_counter() - t0
+    res[f"scan_preprocess_w{W}"]["cpu_baseline"] = {
+        "value": len(scans) / dt, "unit": "scans/s", "cores": 1, "kind": "port",
+        "sample": f"{len(scans)} scans: numpy dataset preprocess + nearest resize (datasets/kitti.py:54-78; one DataLoader "
+                  "worker's share) and preprocess_reals' torch ops on CPU"}
 
 
 def bench_real_side(device, hbm_gbs, peak_src):
@@ -447,6 +486,13 @@ def main():
     alg_flops = entries * flops_per_entry / world                           # per launch, this GPU's share
     exe_entries = (2 * N) * (2 * N + 1) / 2                                 # stacked upper triangle incl. diagonal
     exe_flops = exe_entries * flops_per_entry / world
+    merged = None
+    if args.full_resolution:
+        # un-sampled clouds: every cloud's (0,0,0) points are scanned as one weighted point
+        # (DUSTY_MATRIX_MERGE_ORIGIN), so the executed pair count is data dependent: count it
+        kept = torch.cat([(c != 0).any(-1).sum(1) + ((c == 0).all(-1).any(1)).long() for c in (ref, gen)]).double()
+        exe_flops = 12.0 * float((kept.sum() ** 2 + (kept ** 2).sum()) / 2) / world
+        merged = {"points_scanned_mean": float(kept.mean()), "points_per_cloud": P}
     peak_nominal = SM_COUNT * FP32_LANES * 2 * sm_max_mhz * 1e6 / 1e12
     sink = torch.zeros(1, device=device)
     import ctypes as C
@@ -465,7 +511,7 @@ def main():
         "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json holds no FP32 figure)",
         "peak_probe_ffma_only": peak_probe, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step,
         "algorithmic_flops_per_entry": flops_per_entry, "entries_per_launch_algorithmic": entries / world,
-        "entries_per_launch_executed": exe_entries / world,
+        "entries_per_launch_executed": exe_entries / world, "merged_origin": merged,
         "traffic": ncu_traffic("chamfer_nn_kernel_n1000") if (world == 1 and N == N_CLOUDS) else None,
         "note": "algorithmic = 3 N^2 entries x 12 P^2 flop (what the reference fills); executed = stacked upper triangle "
                 "(M_rr and M_gg are symmetric, SURVEY.md S8), same 12 P^2 flop per entry"}

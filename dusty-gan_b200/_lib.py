@@ -39,7 +39,7 @@ class ScanParams(C.Structure):
 
 
 NOISE_NONE, NOISE_LOGISTIC, NOISE_UNIFORM = 0, 1, 2
-MATRIX_SYMMETRIC, MATRIX_MIRROR, MATRIX_COMPACT_ROWS, MATRIX_PREPARED = 1, 2, 4, 8
+MATRIX_SYMMETRIC, MATRIX_MIRROR, MATRIX_COMPACT_ROWS, MATRIX_PREPARED, MATRIX_MERGE_ORIGIN = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); kept in one table so the symbol-export test can walk it
 SIGNATURES = {

@@ -48,6 +48,9 @@ struct Params {
   long long ldm;
   // batch front end
   float* dist1; float* dist2;
+  // merged-origin clouds (matrix front end, DUSTY_MATRIX_MERGE_ORIGIN) reuse idx1 / idx2 as the per-cloud
+  // int2 {points kept, weight of the last kept point} tables of the X / Y side: the struct keeps the
+  // size the dense kernel was tuned with (two more parameter words changed ptxas' register allocation)
   int* idx1; int* idx2;
 };
 
@@ -66,7 +69,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
-template <int R, bool MATRIX>
+template <int R, bool MATRIX, bool MERGED>
 __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* const tiles = reinterpret_cast<float4*>(smem_raw);
@@ -94,8 +97,17 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
   const float4* const sx = p.scanX + (long long)ci * p.strideX;
   const float4* const sy = p.scanY + (long long)cj * p.strideY;
 
-  const int ntX = (p.paddedX + TILE - 1) / TILE, ntY = (p.paddedY + TILE - 1) / TILE;
-  const int nrbX = (p.countX + RB - 1) / RB, nrbY = (p.countY + RB - 1) / RB;
+  // points actually scanned per cloud; with merged origins the last one stands for `wlast` identical
+  // (0,0,0) points of the original cloud (means still divide by the full count)
+  int2 mx = make_int2(p.countX, 1), my = make_int2(p.countY, 1);
+  if (MERGED) { mx = reinterpret_cast<const int2*>(p.idx1)[ci]; my = reinterpret_cast<const int2*>(p.idx2)[cj]; }
+#define K_countX (MERGED ? mx.x : p.countX)
+#define K_countY (MERGED ? my.x : p.countY)
+#define K_paddedX (MERGED ? (mx.x + CHUNK - 1) / CHUNK * CHUNK : p.paddedX)
+#define K_paddedY (MERGED ? (my.x + CHUNK - 1) / CHUNK * CHUNK : p.paddedY)
+
+  const int ntX = (K_paddedX + TILE - 1) / TILE, ntY = (K_paddedY + TILE - 1) / TILE;
+  const int nrbX = (K_countX + RB - 1) / RB, nrbY = (K_countY + RB - 1) / RB;
   const int seg0 = nrbX * ntY;
   int pos_begin, pos_end;
   if (MATRIX) { pos_begin = 0; pos_end = seg0 + nrbY * ntX; }
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     int dir, t;
     if (pos < seg0) { dir = 0; t = pos % ntY; } else { dir = 1; t = (pos - seg0) % ntX; }
     const float4* src = (dir == 0 ? sy : sx) + (long long)t * TILE;
-    const int padded = dir == 0 ? p.paddedY : p.paddedX;
+    const int padded = dir == 0 ? K_paddedY : K_paddedX;
     const int npts = min(TILE, padded - t * TILE);
     mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u);
     bulk_g2s(tiles + buf * TILE, src, (uint32_t)npts * 16u, &bars[buf]);
@@ -131,8 +143,8 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     if (pos < seg0) { dir = 0; rb = pos / ntY; t = pos - rb * ntY; nt = ntY; }
     else { dir = 1; const int q = pos - seg0; rb = q / ntX; t = q - rb * ntX; nt = ntX; }
     const float4* const rows = dir == 0 ? sx : sy;
-    const int rowcount = dir == 0 ? p.countX : p.countY;
-    const int scanpadded = dir == 0 ? p.paddedY : p.paddedX;
+    const int rowcount = dir == 0 ? K_countX : K_countY;
+    const int scanpadded = dir == 0 ? K_paddedY : K_paddedX;
 
     if (t == 0) {
       #pragma unroll
@@ -240,7 +252,8 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
         const int row = rb * RB + r * TPB + tid;
         if (row < rowcount) {
           if (MATRIX) {
-            dsum += (double)eb[r];
+            if (MERGED) dsum += (row == rowcount - 1 ? (double)(dir == 0 ? mx.y : my.y) : 1.0) * (double)eb[r];
+            else dsum += (double)eb[r];
           } else {
             float* dist = dir == 0 ? p.dist1 : p.dist2;
             int* idx = dir == 0 ? p.idx1 : p.idx2;
@@ -264,6 +277,11 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     }
   }
 }
+
+#undef K_countX
+#undef K_countY
+#undef K_paddedX
+#undef K_paddedY
 
 // xyz (clouds, count, 3) -> scan format (clouds, padded/2, 2) float4; padding is NaN so that it
 // never wins a min (FMNMX returns the non-NaN operand).
@@ -290,6 +308,51 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ xyz
   }
   out[g * 2] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
   out[g * 2 + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+}
+
+// Scan format with merged origins (one CTA per cloud): the points that are not exactly (0,0,0) keep
+// their order, all (0,0,0) points -- dropped pixels of an un-sampled cloud, SURVEY.md S7 -- collapse
+// into ONE origin point appended last, whose multiplicity goes to meta[c].y. A nearest-neighbour
+// minimum does not depend on duplicate candidates and identical rows have identical minima, so the
+// sums over the original cloud are recovered exactly by weighting that row.
+__global__ void __launch_bounds__(256) prep_merge_kernel(const float* __restrict__ xyz, int count, long long stride,
+                                                         float4* __restrict__ out, int2* __restrict__ meta) {
+  __shared__ int wsum[8];
+  __shared__ int s_total;
+  const long long c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* src = xyz + c * count * 3;
+  float* dst = reinterpret_cast<float*>(out + c * stride);
+  const int per = (count + 255) / 256;                // consecutive points per thread: order is preserved
+  const int begin = min(tid * per, count), end = min(begin + per, count);
+  int mine = 0;
+  for (int i = begin; i < end; ++i) mine += (src[3 * i] != 0.0f) || (src[3 * i + 1] != 0.0f) || (src[3 * i + 2] != 0.0f);
+  int inc = mine;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int before = 0, total = 0;
+  #pragma unroll
+  for (int w = 0; w < 8; ++w) { if (w < warp) before += wsum[w]; total += wsum[w]; }
+  auto put = [&](int pos, float x, float y, float z, float n) {
+    float* q = dst + (size_t)(pos >> 1) * 8 + (pos & 1);     // {x0,x1,y0,y1}{z0,z1,n0,n1}
+    q[0] = x; q[2] = y; q[4] = z; q[6] = n;
+  };
+  int pos = before + inc - mine;
+  for (int i = begin; i < end; ++i) {
+    const float x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+    if (x != 0.0f || y != 0.0f || z != 0.0f) put(pos++, x, y, z, fmaf(z, z, fmaf(x, x, y * y)));
+  }
+  const int zeros = count - total;
+  const int kept = total + (zeros > 0 ? 1 : 0);
+  if (tid == 0) {
+    if (zeros > 0) put(total, 0.0f, 0.0f, 0.0f, 0.0f);
+    meta[c] = make_int2(kept, zeros > 0 ? zeros : 1);
+  }
+  const float nan = __int_as_float(0x7fc00000);
+  const int padded = (kept + CHUNK - 1) / CHUNK * CHUNK;
+  for (int i = kept + tid; i < padded; i += 256) put(i, nan, nan, nan, nan);
 }
 
 // Reference ChamferDistanceGradKernel (chamfer_distance.cu:148-172): own-term stores plus
@@ -327,26 +390,26 @@ static int pick_r(int maxcount) {
   return 1;
 }
 
-template <int R, bool MATRIX>
+template <int R, bool MATRIX, bool MERGED>
 static int launch_nn(const Params& p, dim3 grid, cudaStream_t st) {
-  static bool configured[kMaxDevices] = {};   // per (R, MATRIX) instantiation and device: the attribute is per context
+  static bool configured[kMaxDevices] = {};   // per instantiation and device: the attribute is per context
   const int dev = current_device();
   if (!configured[dev]) {
-    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured[dev] = true;
   }
-  nn_kernel<R, MATRIX><<<grid, TPB, SMEM_BYTES, st>>>(p);
+  nn_kernel<R, MATRIX, MERGED><<<grid, TPB, SMEM_BYTES, st>>>(p);
   DUSTY_AFTER_LAUNCH("chamfer nn_kernel");
   return 0;
 }
 
-template <bool MATRIX>
+template <bool MATRIX, bool MERGED>
 static int dispatch_nn(int r, const Params& p, dim3 grid, cudaStream_t st) {
   switch (r) {
-    case 8: return launch_nn<8, MATRIX>(p, grid, st);
-    case 4: return launch_nn<4, MATRIX>(p, grid, st);
-    case 2: return launch_nn<2, MATRIX>(p, grid, st);
-    default: return launch_nn<1, MATRIX>(p, grid, st);
+    case 8: return launch_nn<8, MATRIX, MERGED>(p, grid, st);
+    case 4: return launch_nn<4, MATRIX, MERGED>(p, grid, st);
+    case 2: return launch_nn<2, MATRIX, MERGED>(p, grid, st);
+    default: return launch_nn<1, MATRIX, MERGED>(p, grid, st);
   }
 }
 
@@ -356,6 +419,15 @@ static int run_prep(const float* xyz, long long clouds, int count, float4* out, 
   if (work == 0) return 0;
   prep_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(xyz, clouds, count, padded, out);
   DUSTY_AFTER_LAUNCH("chamfer prep_kernel");
+  return 0;
+}
+
+static size_t meta_bytes(long long clouds) { return align_up((size_t)clouds * sizeof(int2), 256); }
+
+static int run_prep_merge(const float* xyz, long long clouds, int count, float4* out, int2* meta, cudaStream_t st) {
+  if (clouds == 0) return 0;
+  prep_merge_kernel<<<(unsigned)clouds, 256, 0, st>>>(xyz, count, padded_of(count), out, meta);
+  DUSTY_AFTER_LAUNCH("chamfer prep_merge_kernel");
   return 0;
 }
 
@@ -400,7 +472,7 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
   p.dist1 = dist1; p.dist2 = dist2; p.idx1 = idx1; p.idx2 = idx2;
   const int r = pick_r(n > m ? n : m);
   const int rbmax = ((n > m ? n : m) + TPB * r - 1) / (TPB * r);
-  return dispatch_nn<false>(r, p, dim3(rbmax, b, 2), st);
+  return dispatch_nn<false, false>(r, p, dim3(rbmax, b, 2), st);
 }
 
 extern "C" size_t dusty_chamfer_backward_workspace_bytes(int, int, int) { return 0; }
@@ -429,8 +501,8 @@ extern "C" int dusty_chamfer_backward(const float* xyz1, const float* xyz2, int 
 
 extern "C" size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, int pb) {
   size_t s = 0;
-  if (na > 0 && pa > 0) s += align_up(scan_bytes(na, pa), 256);
-  if (nb > 0 && pb > 0) s += align_up(scan_bytes(nb, pb), 256);
+  if (na > 0 && pa > 0) s += align_up(scan_bytes(na, pa), 256) + meta_bytes(na);
+  if (nb > 0 && pb > 0) s += align_up(scan_bytes(nb, pb), 256) + meta_bytes(nb);
   return s;
 }
 
@@ -440,6 +512,7 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int symmetric = (flags & DUSTY_MATRIX_SYMMETRIC) != 0, mirror = (flags & DUSTY_MATRIX_MIRROR) != 0;
   const int compact_rows = (flags & DUSTY_MATRIX_COMPACT_ROWS) != 0, prepared = (flags & DUSTY_MATRIX_PREPARED) != 0;
+  const int merge = (flags & DUSTY_MATRIX_MERGE_ORIGIN) != 0;
   if (mirror && (!symmetric || compact_rows)) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: MIRROR needs SYMMETRIC and excludes COMPACT_ROWS");
   if (na < 0 || nb < 0 || pa <= 0 || pb <= 0) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: bad sizes na=%d pa=%d nb=%d pb=%d", na, pa, nb, pb);
   if (symmetric && (nb != na || pb != pa)) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: symmetric needs nb==na and pb==pa");
@@ -451,11 +524,21 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   if (!aligned16(workspace)) return fail_arg(DUSTY_EALIGN, "chamfer_matrix: workspace must be 16-byte aligned");
   const size_t need = dusty_chamfer_matrix_workspace_bytes(na, pa, symmetric ? 0 : nb, pb);
   if (workspace_bytes < need) return fail_arg(DUSTY_ENOSPACE, "chamfer_matrix: workspace %zu < %zu", workspace_bytes, need);
-  float4* sa = static_cast<float4*>(workspace);
-  float4* sb = symmetric ? sa : reinterpret_cast<float4*>(static_cast<char*>(workspace) + align_up(scan_bytes(na, pa), 256));
+  // workspace: [scan A][meta A]([scan B][meta B])
+  char* const wsp = static_cast<char*>(workspace);
+  float4* sa = reinterpret_cast<float4*>(wsp);
+  int2* ma = reinterpret_cast<int2*>(wsp + align_up(scan_bytes(na, pa), 256));
+  char* const wsb = wsp + align_up(scan_bytes(na, pa), 256) + meta_bytes(na);
+  float4* sb = symmetric ? sa : reinterpret_cast<float4*>(wsb);
+  int2* mb = symmetric ? ma : reinterpret_cast<int2*>(wsb + align_up(scan_bytes(nb, pb), 256));
   if (!prepared) {
-    if (int rc = run_prep(A, na, pa, sa, st)) return rc;
-    if (!symmetric) if (int rc = run_prep(B, nb, pb, sb, st)) return rc;
+    if (merge) {
+      if (int rc = run_prep_merge(A, na, pa, sa, ma, st)) return rc;
+      if (!symmetric) if (int rc = run_prep_merge(B, nb, pb, sb, mb, st)) return rc;
+    } else {
+      if (int rc = run_prep(A, na, pa, sa, st)) return rc;
+      if (!symmetric) if (int rc = run_prep(B, nb, pb, sb, st)) return rc;
+    }
   }
   const int rows = (row_end - row_begin + row_stride - 1) / row_stride;
   if (rows > 65535) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: %d rows in one call exceeds 65535", rows);
@@ -467,5 +550,10 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   p.row_begin = row_begin; p.row_stride = row_stride;
   p.symmetric = symmetric; p.mirror = mirror; p.compact_rows = compact_rows;
   p.M = M; p.ldm = ldm;
-  return dispatch_nn<true>(pick_r(pa > pb ? pa : pb), p, dim3(nb, rows, 1), st);
+  const dim3 grid(nb, rows, 1);
+  if (merge) {
+    p.idx1 = reinterpret_cast<int*>(ma); p.idx2 = reinterpret_cast<int*>(mb);
+    return dispatch_nn<true, true>(pick_r(pa > pb ? pa : pb), p, grid, st);
+  }
+  return dispatch_nn<true, false>(pick_r(pa > pb ? pa : pb), p, grid, st);
 }

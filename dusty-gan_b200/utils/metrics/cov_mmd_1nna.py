@@ -31,10 +31,18 @@ def _check_clouds(pcs, name):
     return pcs.contiguous()
 
 
-def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None):
+# Clouds with more points than this are taken to be un-sampled range images, whose dropped pixels are
+# all the same (0,0,0) point (reference evaluate_reconstruction.py:124-131): the kernel
+# then scans one origin point of that multiplicity per cloud. The choice depends on the shape only, so
+# a given input always takes the same path (and every row shard of a matrix the same one).
+MERGE_ORIGIN_ABOVE = 4096
+
+
+def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None, merge_origin=None):
     """M[i,j] = compute_cd(pcs_1[i], pcs_2[j]) in one launch. ``pcs_2=None`` declares the symmetric
     case (upper triangle computed, mirrored unless ``compact_rows``). ``rows=(begin,end,stride)``
-    restricts the computation to a row shard."""
+    restricts the computation to a row shard. ``merge_origin`` (default: by point count, see
+    ``MERGE_ORIGIN_ABOVE``) collapses each cloud's exactly-zero points into one weighted point."""
     a = _check_clouds(pcs_1, "pcs_1")
     symmetric = pcs_2 is None
     b = a if symmetric else _check_clouds(pcs_2, "pcs_2")
@@ -49,6 +57,10 @@ def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None):
             flags |= _lib.MATRIX_MIRROR
     if compact_rows:
         flags |= _lib.MATRIX_COMPACT_ROWS
+    if merge_origin is None:
+        merge_origin = max(pa, pb) > MERGE_ORIGIN_ABOVE
+    if merge_origin:
+        flags |= _lib.MATRIX_MERGE_ORIGIN
     if out is None:
         out = torch.zeros(nrows if compact_rows else na, nb, device=a.device, dtype=torch.float32)
     if na == 0 or nb == 0 or nrows == 0:

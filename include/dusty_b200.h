@@ -110,11 +110,19 @@ DUSTY_API size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, in
  *                                i.e. M is the rank's (rows_owned, nb) block ready for an all-gather
  *                                (incompatible with MIRROR);
  *     DUSTY_MATRIX_PREPARED      the workspace already holds the scan-format copies of these A,B
- *                                from an earlier call: skip rebuilding them. */
+ *                                from an earlier call (with the same MERGE_ORIGIN choice): skip
+ *                                rebuilding them;
+ *     DUSTY_MATRIX_MERGE_ORIGIN  un-sampled clouds keep every dropped pixel as a (0,0,0) point
+ *                                (evaluate_reconstruction.py:124-131). All exactly-zero
+ *                                points of a cloud are scanned as ONE point of that multiplicity:
+ *                                the minima are unchanged (duplicate candidates never change a
+ *                                minimum, identical rows share theirs) and the means still divide
+ *                                by pa / pb, so M is the same matrix for a fraction of the work. */
 #define DUSTY_MATRIX_SYMMETRIC    1
 #define DUSTY_MATRIX_MIRROR       2
 #define DUSTY_MATRIX_COMPACT_ROWS 4
 #define DUSTY_MATRIX_PREPARED     8
+#define DUSTY_MATRIX_MERGE_ORIGIN 16
 DUSTY_API int dusty_chamfer_matrix(const float* A, int na, int pa, const float* B, int nb, int pb,
                          int row_begin, int row_end, int row_stride, int flags,
                          float* M, long long ldm,

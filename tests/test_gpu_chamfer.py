@@ -148,6 +148,41 @@ def test_matrix_unequal_point_counts_and_multi_tile():
     assert rel_err(M, native.pairwise_cd(a, b, rounding="cuda")).max() <= REL_TOL
 
 
+@pytest.mark.parametrize("shape", [(3, 4, 5000, 5000), (2, 3, 6000, 4500), (2, 2, 333, 70)])
+def test_matrix_merged_origin_points(shape):
+    """Un-sampled clouds: collapsing every cloud's (0,0,0) points into one weighted point
+    must give the matrix of the plain kernel (values within double-sum reassociation, i.e. <= 1 ulp of f32)
+    and the oracle's within the tolerance. Includes clouds without zeros, all zeros, -0.0 and one zero."""
+    na, nb, pa, pb = shape
+    a = lidar_like_clouds(na, pa, 601, dropped=0.5); b = lidar_like_clouds(nb, pb, 602, dropped=0.35)
+    a[0][np.all(a[0] == 0, axis=1)] = lidar_like_clouds(1, pa, 603, dropped=0.0)[0][np.all(a[0] == 0, axis=1)]  # no zeros
+    b[0] = 0.0                                                                                                # only zeros
+    b[1][np.all(b[1] == 0, axis=1)] *= -1.0                                                                   # -0.0 is the origin too
+    if na > 2:
+        a[2, 1:] = lidar_like_clouds(1, pa, 604, dropped=0.0)[0, 1:]; a[2, 0] = 0.0                           # a single zero
+    plain = matrix(a, b, merge_origin=False)
+    merged = matrix(a, b, merge_origin=True)
+    O = native.pairwise_cd(a, b, rounding="cuda")
+    assert np.all(np.abs(merged - plain) <= 2.0 ** -23 * np.abs(plain))
+    assert np.abs(merged - O).max() <= REL_TOL * O.max()
+    if pa == pb:
+        S0 = matrix(a, merge_origin=False); S1 = matrix(a, merge_origin=True)
+        assert np.array_equal(S1, S1.T) and np.all(np.diag(S1) == 0)
+        assert np.all(np.abs(S1 - S0) <= 2.0 ** -23 * np.abs(S0))
+        # row shards take the same path: bit-identical to the full launch
+        from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix
+        sub = chamfer_matrix(cuda(a), cuda(b), rows=(1, na, 2), merge_origin=True).cpu().numpy()
+        assert np.array_equal(sub[1::2], merged[1::2])
+
+
+def test_matrix_merge_is_the_default_for_unsampled_clouds():
+    from dusty_gan_b200.utils.metrics import cov_mmd_1nna as M
+    a = lidar_like_clouds(2, M.MERGE_ORIGIN_ABOVE + 4, 611, dropped=0.5)
+    assert np.array_equal(matrix(a), matrix(a, merge_origin=True))
+    s = sampled_clouds(2, 2048, 612)
+    assert np.array_equal(matrix(s), matrix(s, merge_origin=False))
+
+
 def test_matrix_golden_reference_driver(golden):
     g = golden("metrics_cpu.npz")
     assert rel_err(matrix(g["ref"], g["gen"]), g["M_rg"]).max() <= REL_TOL
