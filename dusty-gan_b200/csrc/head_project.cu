@@ -14,6 +14,7 @@
 // run on the same GPU. HBM traffic per pixel: read depth + confidence, write mask + depth + xyz
 // = 28 B (DUSty-I) / 36 B (DUSty-II); the noise map and the trig table are small and L2 resident.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -21,8 +22,8 @@ namespace dusty {
 namespace head {
 
 constexpr int TPB = 256;
-constexpr int ITERS = 4;
-constexpr int SEG = TPB * 4 * ITERS;    // pixels per CTA (4096)
+constexpr int GROUP = TPB * 4;          // pixels per CTA and iteration (1024)
+constexpr int MAX_ITERS = 4;
 
 struct GateDev {
   int mode;
@@ -83,8 +84,11 @@ __device__ __forceinline__ float range_from_inv(float inv, const dusty_head_para
   return __fmul_rn(d, valid ? 1.0f : 0.0f);
 }
 
-template <int C, bool COMPACT>
+// ITERS 4-pixel groups per thread: more independent 128-bit loads in flight per thread against
+// finer CTAs, fewer registers and more resident warps; see pick_iters for the measurement.
+template <int C, bool COMPACT, int ITERS>
 __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
+  constexpr int SEG = GROUP * ITERS;
   __shared__ int wsum[2][TPB / 32];
   __shared__ int s_base;
   __shared__ __align__(16) float xyz_stage[TPB / 32][384];     // per-warp transpose buffer for interleaved points
@@ -319,6 +323,16 @@ __global__ void __launch_bounds__(TPB) gumbel_sigmoid_kernel(const float* __rest
                          gate_value(cv.z, g.mode, na.z, nb.z, p), gate_value(cv.w, g.mode, na.w, nb.w, p)));
 }
 
+// Pixel groups per thread. Measured on B200 (tests/perf_head_iters.py, batch 256 of 64x512, DUSty-I):
+// ITERS = 4 (62 registers, 4 CTAs/SM, 2048 CTAs = 3.46 waves) 43.3 us; ITERS = 2 (42 registers) 39.1 us;
+// ITERS = 1 (32 registers, 8 CTAs/SM = 2048 threads/SM, 8192 CTAs) 37.4 us = 6.29 TB/s. One group per
+// thread wins at every batch size: full occupancy hides the latency that the extra loads per thread
+// were meant to hide, and the last wave is small. DUSTY_HEAD_ITERS=2|4 re-creates the A/B.
+static int pick_iters(int, int) {
+  if (const char* e = getenv("DUSTY_HEAD_ITERS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) return v; }
+  return 1;
+}
+
 static int check_params(const dusty_head_params* p, const char* who) {
   if (!p) return fail_arg(DUSTY_EINVAL, "%s: null params", who);
   if (p->b < 0 || p->h <= 0 || p->w <= 0) return fail_arg(DUSTY_EINVAL, "%s: bad shape b=%d h=%d w=%d", who, p->b, p->h, p->w);
@@ -349,7 +363,7 @@ using namespace dusty::head;
 extern "C" size_t dusty_head_project_workspace_bytes(int b, int h, int w) {
   if (b <= 0 || h <= 0 || w <= 0) return 0;
   const long long npix = (long long)h * w;
-  const long long segs = (npix + SEG - 1) / SEG;
+  const long long segs = (npix + GROUP - 1) / GROUP;      // the finest segmentation any launch uses
   return align_up((size_t)b * segs * sizeof(unsigned), 256);
 }
 
@@ -379,7 +393,9 @@ extern "C" int dusty_head_project(const dusty_head_params* p, const float* depth
   a.out_mask = out_mask; a.out_depth = out_depth; a.out_points = out_points;
   a.out_count = out_count; a.out_index = out_index; a.out_compact = out_compact;
   a.npix = p->h * p->w;
-  a.segs_per_image = (a.npix + SEG - 1) / SEG;
+  const int iters = pick_iters(p->b, a.npix);
+  const int seg = GROUP * iters;
+  a.segs_per_image = (a.npix + seg - 1) / seg;
   const long long ctas = (long long)p->b * a.segs_per_image;
   if (ctas > 0x7fffffffLL) return fail_arg(DUSTY_EINVAL, "head_project: grid too large");
   if (compact) {
@@ -388,13 +404,18 @@ extern "C" int dusty_head_project(const dusty_head_params* p, const float* depth
     a.seg_state = static_cast<unsigned*>(workspace);
     DUSTY_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ctas * sizeof(unsigned), st));
   }
-  if (p->conf_channels == 1) {
-    if (compact) head_project_kernel<1, true><<<(unsigned)ctas, TPB, 0, st>>>(a);
-    else head_project_kernel<1, false><<<(unsigned)ctas, TPB, 0, st>>>(a);
-  } else {
-    if (compact) head_project_kernel<2, true><<<(unsigned)ctas, TPB, 0, st>>>(a);
-    else head_project_kernel<2, false><<<(unsigned)ctas, TPB, 0, st>>>(a);
+#define DUSTY_HEAD_LAUNCH(C, COMPACT)                                                                     \
+  switch (iters) {                                                                                        \
+    case 1: head_project_kernel<C, COMPACT, 1><<<(unsigned)ctas, TPB, 0, st>>>(a); break;                 \
+    case 2: head_project_kernel<C, COMPACT, 2><<<(unsigned)ctas, TPB, 0, st>>>(a); break;                 \
+    default: head_project_kernel<C, COMPACT, 4><<<(unsigned)ctas, TPB, 0, st>>>(a); break;                \
   }
+  if (p->conf_channels == 1) {
+    if (compact) { DUSTY_HEAD_LAUNCH(1, true) } else { DUSTY_HEAD_LAUNCH(1, false) }
+  } else {
+    if (compact) { DUSTY_HEAD_LAUNCH(2, true) } else { DUSTY_HEAD_LAUNCH(2, false) }
+  }
+#undef DUSTY_HEAD_LAUNCH
   DUSTY_AFTER_LAUNCH("head_project_kernel");
   return 0;
 }

@@ -41,7 +41,7 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int size) {
   return s < size - 1 ? s : size - 1;
 }
 
-__global__ void __launch_bounds__(TPB) scan_preprocess_kernel(const Args a) {
+__global__ void __launch_bounds__(TPB, 6) scan_preprocess_kernel(const Args a) {
   __shared__ __align__(16) float xyz_stage[TPB / 32][384];
   const dusty_scan_params& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
