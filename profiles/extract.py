@@ -46,12 +46,17 @@ for rep in (f"prof_chamfer_{R}.ncu-rep", f"prof_stages_{R}.ncu-rep"):
     path = os.path.join(ROOT, "gpurun_out", rep)
     if os.path.exists(path):
         kernels += raw(path)
+    elif rep.startswith("prof_chamfer") and R != "r1":      # dense Chamfer kernel unchanged since r1 (identical SASS): keep its capture
+        kernels += [k for k in json.load(open(os.path.join(ROOT, "profiles", "ncu_r1_metrics.json"))) if "nn_kernel" in k["Kernel Name"][0]]
 json.dump(kernels, open(os.path.join(ROOT, "profiles", f"ncu_{R}_metrics.json"), "w"), indent=1)
 traffic = {}
 for d in kernels:
     name = d["Kernel Name"][0]
-    key = ("chamfer_nn_kernel_n1000" if "nn_kernel" in name else "head_project_dusty1_b256" if "head_project" in name
-           else "fps_kernel_148clouds")
+    key = ("chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0>" in name or "nn_kernel<8, 1>" in name
+           else "chamfer_nn_kernel_merged_24x32768" if "nn_kernel" in name
+           else "head_project_dusty1_b256" if "head_project" in name
+           else "scan_preprocess_256x64x2048" if "scan_preprocess" in name
+           else "fps_multi_888clouds" if "fps_multi" in name else "fps_pruned_148clouds")
     traffic[key] = to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"])
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 

@@ -1,15 +1,23 @@
 #!/bin/bash
 # ncu captures for one round (run on the GPU box through gpurun; see B200_PROFILING.md).
-#   bash profiles/run_ncu.sh r1        -> gpurun_out/launches_r1.csv, gpurun_out/prof_*_r1.ncu-rep
+#   bash profiles/run_ncu.sh r1 [steps]   -> gpurun_out/launches_r1.csv, gpurun_out/prof_*_r1.ncu-rep
+# steps: any of "l" (launch list), "c" (Chamfer dense kernel, full set), "s" (stage kernels, full set); default all
 set -u
 R=${1:-r1}
+STEPS=${2:-lcs}
 mkdir -p gpurun_out
 # 1. every launch of the default bench command with its device time (cold-cache, serialised: compare shares)
+if [[ $STEPS == *l* ]]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${R}.csv \
     python bench.py --steps 2 --warmup 1 --skip-extras > gpurun_out/bench_under_ncu_${R}.log 2>&1
+fi
 # 2. the dominant kernel, full set, at the bench's own size (2 s kernel, ~40 replays)
+if [[ $STEPS == *c* ]]; then
 ncu --set full --clock-control none --import-source on -k regex:nn_kernel -s 1 -c 1 -f -o gpurun_out/prof_chamfer_${R} \
     python bench.py --steps 1 --warmup 1 --skip-extras > gpurun_out/prof_chamfer_${R}.log 2>&1
-# 3. head + projection and FPS kernels
-ncu --set full --clock-control none --import-source on -k regex:"head_project_kernel|fps_" -s 2 -c 2 -f \
+fi
+# 3. head + projection, real-scan preprocess, FPS and the merged-origin Chamfer kernel (last launch of each)
+if [[ $STEPS == *s* ]]; then
+ncu --set full --clock-control none --import-source on -k regex:"head_project_kernel|fps_|scan_preprocess|nn_kernel" -s 5 -c 5 -f \
     -o gpurun_out/prof_stages_${R} python profiles/stage_driver.py > gpurun_out/prof_stages_${R}.log 2>&1
+fi

@@ -1,4 +1,7 @@
-"""Tiny driver for ncu: a few launches of the head+projection kernel (batch 256) and the FPS kernel."""
+"""Tiny driver for ncu: the stage kernels at their bench sizes. run_ncu.sh skips the first five matching
+launches (warm-up: head x3, FPS multi, scan preprocess) and captures the next five:
+head+projection (batch 256), scan preprocess (256 scans, full width), FPS pruned (148 clouds),
+FPS multi (888 clouds), merged-origin Chamfer matrix (24 un-sampled clouds)."""
 import os
 import sys
 
@@ -7,15 +10,32 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from dusty_gan_b200 import pipeline  # noqa: E402
+from dusty_gan_b200.datasets import preprocess_scans  # noqa: E402
+from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix  # noqa: E402
 from dusty_gan_b200.utils.sampling.fps import downsample_point_clouds  # noqa: E402
 
 dev = torch.device("cuda:0")
 lidar = bench.make_lidar(dev)
 head = bench.make_head(1, dev)
-depth, conf = bench.backbone_like(256, 1, 11, dev)
-for _ in range(3):
-    out = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)
-pts = out["points"][:148].contiguous()
-for _ in range(2):
-    downsample_point_clouds(pts, 2048)
+depth, conf = bench.backbone_like(888, 1, 11, dev)
+d256, c256 = depth[:256].contiguous(), conf[:256].contiguous()
+scans = torch.randn(256, 64, 2048, 4, device=dev) * 20
+
+
+def head256():
+    return pipeline.maskout_and_project(head, {"depth": d256, "confidence": c256}, lidar, tol=0.0)
+
+
+# ---- warm-up: five matching launches ----
+head256(); head256()
+pts = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"]
+downsample_point_clouds(pts, 2048)
+preprocess_scans(scans, (64, 2048), 0.9, 120.0, -1)
+torch.cuda.synchronize()
+# ---- captured ----
+head256()
+preprocess_scans(scans, (64, 2048), 0.9, 120.0, -1)
+downsample_point_clouds(pts[:148].contiguous(), 2048)
+downsample_point_clouds(pts, 2048)
+chamfer_matrix(pts[:24].contiguous())
 torch.cuda.synchronize()
