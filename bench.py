@@ -220,18 +220,27 @@ def bench_stages(device, hbm_gbs, peak_src, flush):
     ms = time_events(img2cloud, 3, 1)
     res["range_image_to_fps_clouds_per_s"] = n_fps / (statistics.median(ms) * 1e-3)
     res.update(bench_real_side(device, hbm_gbs, peak_src))
+    # JSD of the two occupancy histograms (next row 8f-2) on 1000 vs 1000 sampled clouds, as
+    # evaluate_synthesis.py:174-177 calls it (clouds halved into the unit sphere)
+    from dusty_gan_b200.utils.metrics.jsd import compute_jsd
+    sampled = downsample_point_clouds(pts, N_POINTS) / 2.0
+    ja, jb = sampled[:444].repeat(3, 1, 1)[:1000].contiguous(), sampled[444:].repeat(3, 1, 1)[:1000].contiguous()
+    compute_jsd(ja, jb)
+    ms = statistics.median(time_events(lambda: compute_jsd(ja, jb), 5, 1))
+    res["jsd"] = {"clouds_per_s": 2000 / (ms * 1e-3), "ms": ms, "clouds": 2000, "points": N_POINTS, "grid": "28^3 in-sphere (9261 cells)",
+                  "note": "two voting launches + one reduction, including the 4-byte read-back of the score"}
     try:
-        stage_cpu_baselines(res, head, lidar, depth[:32], conf[:32], pts[:2])
+        stage_cpu_baselines(res, head, lidar, depth[:32], conf[:32], pts[:2], sampled[:4])
     except Exception as exc:        # the checker is optional for the measurement
         res["cpu_baselines_error"] = repr(exc)[:200]
     return res
 
 
-def stage_cpu_baselines(res, head, lidar, depth, conf, pts):
+def stage_cpu_baselines(res, head, lidar, depth, conf, pts, jsd_clouds):
     """cpu_baseline leg of the stages: the reference's op chains on the host cores, bounded
     samples. The head/projection/real-data chains are the reference's PyTorch/numpy ops (oracle restatement,
     kind "port"); the reference has NO CPU FPS (fps/...cpp:96), so that line is the oracle's C replay."""
-    from oracle import head_projection as hp, native, real_data as rd
+    from oracle import head_projection as hp, jsd as ojsd, native, real_data as rd
     threads = torch.get_num_threads()
     d, c = depth.cpu(), conf.cpu()
     noise, angle = head.gumbel.fixed_noise.cpu(), lidar.angle.cpu()
@@ -251,6 +260,12 @@ def stage_cpu_baselines(res, head, lidar, depth, conf, pts):
         "value": len(p) / dt, "unit": "clouds/s", "cores": 1, "kind": "port",
         "sample": f"{len(p)} clouds of {H * W} points -> {N_POINTS}: oracle's single-thread C replay of the reference "
                   "CUDA kernel (the reference has no CPU FPS)"}
+    jc = jsd_clouds.cpu().numpy()
+    t0 = time.perf_counter(); ojsd.vote(jc); dt = time.perf_counter() - t0
+    res["jsd"]["cpu_baseline"] = {
+        "value": len(jc) / dt, "unit": "clouds/s", "cores": 1, "kind": "port",
+        "sample": f"{len(jc)} clouds x {jc.shape[1]} points: brute-force arg-min against the 9261 grid points "
+                  "(reference utils/metrics/jsd.py:42-84) in numpy"}
     scans = rd.synthetic_scans(4, seed=1)
     t0 = time.perf_counter()
     items = [rd.dataset_item(x, (H, W)) for x in scans]
