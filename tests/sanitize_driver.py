@@ -42,5 +42,15 @@ gen = downsample_point_clouds(torch.from_numpy(lidar_like_clouds(5, 2000, 3)).cu
 ref = downsample_point_clouds(torch.from_numpy(lidar_like_clouds(4, 2000, 4)).cuda(), 300)
 print(compute_cov_mmd_1nna(gen, ref, 512, ("cd",), verbose=False))
 print(compute_jsd(gen / 2, ref / 2))
+# real-data side and the merged-origin Chamfer matrix
+from dusty_gan_b200.datasets import preprocess_scans  # noqa: E402
+from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix  # noqa: E402
+scans = (torch.randn(2, 8, 96, 4, device="cuda") * 20) * (torch.rand(2, 8, 96, 1, device="cuda") > 0.3)
+preprocess_scans(scans, (8, 24), want=("xyz", "depth", "mask", "inv", "points"))
+preprocess_scans(scans[..., :3].contiguous(), (8, 96))
+u = torch.from_numpy(lidar_like_clouds(3, 2300, 6, dropped=0.5)).cuda()
+u[1] = 0
+print(chamfer_matrix(u, merge_origin=True))
+print(chamfer_matrix(u, u[:2, :600].contiguous(), merge_origin=True))
 torch.cuda.synchronize()
 print("sanitize driver done")
