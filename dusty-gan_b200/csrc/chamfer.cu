@@ -23,6 +23,7 @@
 //            in different chunks are closer to each other than the search's rounding error
 //            (~2^-23 (|a|^2+|b|^2)), in which case it exceeds the minimum by at most that much.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -470,8 +471,15 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
   p.paddedX = padded_of(n); p.paddedY = padded_of(m);
   p.strideX = p.paddedX; p.strideY = p.paddedY;
   p.dist1 = dist1; p.dist2 = dist2; p.idx1 = idx1; p.idx2 = idx2;
-  const int r = pick_r(n > m ? n : m);
-  const int rbmax = ((n > m ? n : m) + TPB * r - 1) / (TPB * r);
+  // rows per thread: the largest R that still gives about one CTA per SM (a CTA covers 256 R rows of one
+  // direction of one pair); few pairs of small clouds otherwise leave most of the GPU idle. Measured
+  // (tests/perf_chamfer_batch.py, 32 pairs of 2048 points): R = 8 (64 CTAs) 133 us, R = 4 (128 CTAs) 91 us,
+  // R = 1 (512 CTAs) 117 us -- smaller R feeds fewer FFMA2 per LDS, so stop as soon as the GPU is covered.
+  const int big = n > m ? n : m;
+  int r = pick_r(big);
+  while (r > 1 && 2LL * b * ((big + TPB * r - 1) / (TPB * r)) < 120) r >>= 1;
+  if (const char* e = getenv("DUSTY_CHAMFER_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) r = v; }
+  const int rbmax = (big + TPB * r - 1) / (TPB * r);
   return dispatch_nn<false, false>(r, p, dim3(rbmax, b, 2), st);
 }
 

@@ -58,6 +58,35 @@ def main():
     out["chamfer_ours_entries_per_s_same_shape"] = 64 * 512 / t_ours
     err = (ref_rows() - chamfer_matrix(clouds[:64].contiguous(), big)).abs().max().item()
     out["chamfer_max_abs_diff"] = err
+    # batch front end (per-point dist + idx, forward and backward) as evaluate_reconstruction.py:124-131 and
+    # demo.py:510-515 use it: 32 pairs of sampled clouds, and 8 pairs of un-sampled 32768-point clouds
+    from dusty_gan_b200.utils.metrics.distance import chamfer_distance
+    for tag, a, b in (("2048", clouds[:32].contiguous(), clouds[32:64].contiguous()),
+                      ("32768", pts[:8].contiguous(), pts[8:16].contiguous())):
+        B, n, _ = a.shape
+
+        def ref_fwd():
+            d1 = torch.zeros(B, n, device=dev); d2 = torch.zeros(B, n, device=dev)
+            i1 = torch.zeros(B, n, dtype=torch.int, device=dev); i2 = torch.zeros(B, n, dtype=torch.int, device=dev)
+            cd.forward_cuda(a, b, d1, d2, i1, i2)
+            return d1, d2, i1, i2
+        d1, d2, i1, i2 = ref_fwd()
+        g = torch.ones(B, n, device=dev)
+
+        def ref_bwd():
+            g1 = torch.zeros_like(a); g2 = torch.zeros_like(b)
+            cd.backward_cuda(a, b, g1, g2, g, g, i1, i2)
+            return g1, g2
+        out[f"batch{tag}_ref_fwd_pairs_per_s"] = B / timed(ref_fwd)
+        out[f"batch{tag}_ours_fwd_pairs_per_s"] = B / timed(lambda: chamfer_distance(a, b))
+        o1, o2 = chamfer_distance(a, b)
+        out[f"batch{tag}_fwd_bit_equal_frac"] = float(((o1 == d1).float().mean() + (o2 == d2).float().mean()) / 2)
+        out[f"batch{tag}_ref_bwd_pairs_per_s"] = B / timed(ref_bwd)
+        ar = a.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+        with torch.enable_grad():
+            q1, q2 = chamfer_distance(ar, br)
+            loss = q1.sum() + q2.sum()
+        out[f"batch{tag}_ours_bwd_pairs_per_s"] = B / timed(lambda: torch.autograd.grad(loss, (ar, br), retain_graph=True))
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "ref_gpu.json"), "w") as fh:
