@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
   // (0,0,0) points of the original cloud (means still divide by the full count)
   int2 mx = make_int2(p.countX, 1), my = make_int2(p.countY, 1);
   if (MERGED) { mx = reinterpret_cast<const int2*>(p.idx1)[ci]; my = reinterpret_cast<const int2*>(p.idx2)[cj]; }
+// Merged clouds have arbitrary point counts, so the last row block of a direction is usually almost empty
+// (16 390 points = 8 full blocks + 6 rows). There a warp owns 32 R consecutive rows, and a warp without
+// live rows skips the search: the FMA pipe it would have occupied goes to the SM's other resident CTA.
+#define K_ROW(r) (MERGED ? rb * RB + (tid >> 5) * (32 * R) + (r) * 32 + lane : rb * RB + (r) * TPB + tid)
 #define K_countX (MERGED ? mx.x : p.countX)
 #define K_countY (MERGED ? my.x : p.countY)
 #define K_paddedX (MERGED ? (mx.x + CHUNK - 1) / CHUNK * CHUNK : p.paddedX)
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     if (t == 0) {
       #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int row = rb * RB + r * TPB + tid;
+        const int row = K_ROW(r);
         const int rr = row < rowcount ? row : 0;
         const float4 a0 = rows[(rr >> 1) * 2], a1 = rows[(rr >> 1) * 2 + 1];
         const bool hi = rr & 1;
@@ -167,6 +171,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     const float4* const tp = tiles + buf * TILE;
     const int nch = min(TILE, scanpadded - t * TILE) / CHUNK;
 
+    if (!MERGED || rb * RB + (tid >> 5) * (32 * R) < rowcount) {      // warp-uniform
     // ---- search: which chunk of this tile holds the smallest |b|^2 - 2 a.b ----
     float cur[R];
     int cid[R];
@@ -246,11 +251,13 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
       }
     }
 
+    }
+
     // ---- end of a (direction, row block): emit ----
     if (t == nt - 1) {
       #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int row = rb * RB + r * TPB + tid;
+        const int row = K_ROW(r);
         if (row < rowcount) {
           if (MATRIX) {
             if (MERGED) dsum += (row == rowcount - 1 ? (double)(dir == 0 ? mx.y : my.y) : 1.0) * (double)eb[r];
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
   }
 }
 
+#undef K_ROW
 #undef K_countX
 #undef K_countY
 #undef K_paddedX
