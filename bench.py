@@ -165,7 +165,7 @@ def time_events(fn, iters, warmup, flush=None):
     return ms
 
 
-def bench_stages(device, hbm_gbs, peak_src, flush):
+def bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz=1965.0):
     """configs[1] and the range-image -> FPS stage on one GPU."""
     from dusty_gan_b200 import pipeline
     from dusty_gan_b200.utils.sampling.fps import downsample_point_clouds
@@ -213,7 +213,12 @@ def bench_stages(device, hbm_gbs, peak_src, flush):
     res["fps"] = {"clouds_per_s": n_fps / t, "ms": t * 1e3, "clouds": n_fps, "points_in": H * W, "points_out": N_POINTS,
                   "eligible_mean": float(elig.mean()), "eligible_max": float(elig.max()),
                   "nominal_updates_per_s": float(elig.sum()) * (N_POINTS - 1) / t,
-                  "note": "nominal = eligible points x (samples-1); the pruned kernel skips buckets whose lower bound rules out a change"}
+                  # ceilings of an un-pruned kernel, per eligible-point update
+                  "ceilings_updates_per_s": {"shared_memory_12B_per_update": SM_COUNT * 128 * sm_max_mhz * 1e6 / 12,
+                                             "fp32_issue_8_ops_per_update": SM_COUNT * FP32_LANES * sm_max_mhz * 1e6 / 8},
+                  "note": "nominal = eligible points x (samples-1); the pruned kernel skips buckets whose lower bound rules out a "
+                          "change (about 94 % of them), which is how the nominal rate exceeds both ceilings of a kernel that "
+                          "touches every point every iteration; the kernel itself is latency bound (profiles/SUMMARY_r1.md)"}
 
     def img2cloud():
         pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, N_POINTS, tol=0.0)
@@ -551,7 +556,7 @@ def main():
 
     if world == 1 and not args.skip_extras:
         try:
-            line["stages"] = bench_stages(device, hbm_gbs, peak_src, flush)
+            line["stages"] = bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz)
         except Exception as exc:  # the headline line must still be printed
             line["stages"] = {"error": repr(exc)[:300]}
         # bounded CPU sample: 16 x 16 entries of this very workload through the reference as shipped

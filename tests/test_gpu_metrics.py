@@ -104,3 +104,44 @@ def test_generate_and_evaluate_slice():
     expect = om.compute_cov_mmd_1nna(sets["gen"].cpu().numpy(), sets["ref"].cpu().numpy())
     for k in KEYS:
         assert scores[k] == pytest.approx(expect[k], rel=1e-5, abs=1e-12), k
+
+
+def test_config0_64_vs_64_at_full_size():
+    """BASELINE configs[0] at its own size: 64 vs 64 range images of 64x512 through the DUSty-I head,
+    projection and FPS to 2048 points, then every entry of M_rr / M_rg / M_gg and every score against the
+    oracle (the C restatement in the reference CUDA kernel's rounding, rows spread over host threads --
+    ctypes releases the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    from dusty_gan_b200.models.dusty import DUSty1
+    from dusty_gan_b200.utils.lidar import LiDAR, synthetic_hdl64e_angles
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import compute_cov_mmd_1nna, pairwise_matrices
+    from dusty_gan_b200 import pipeline
+    H, W, P, N = 64, 512, 2048, 64
+    lidar = LiDAR(H, W, 0.9, 120.0, angle=synthetic_hdl64e_angles()).cuda()
+    head = DUSty1(torch.nn.Identity(), tau=1.0).cuda().eval()
+    sets = {}
+    for name, seed in (("gen", 11), ("ref", 12)):
+        depth, conf, u1, u2 = head_inputs(N, 1, H, W, seed, "cuda")
+        if head.gumbel.fixed_noise is None:
+            head.gumbel.fixed_noise = head.gumbel._logistic_from_uniform(u1, u2)
+        sets[name] = pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, P, tol=0.0)[0]
+    gen, ref = sets["gen"], sets["ref"]
+    scores = compute_cov_mmd_1nna(gen, ref, 512, ("cd",), verbose=False)
+    Mrr, Mrg, Mgg = [m.cpu().numpy() for m in pairwise_matrices(gen, ref)]
+    stacked = np.concatenate([ref.cpu().numpy(), gen.cpu().numpy()])
+    workers = min(32, os.cpu_count() or 1)
+    rows = [(r, min(r + 4, 2 * N)) for r in range(0, 2 * N, 4)]
+    with ThreadPoolExecutor(workers) as pool:
+        parts = list(pool.map(lambda rr: native.pairwise_cd(stacked, None, rows=rr, rounding="cuda"), rows))
+    U = np.zeros((2 * N, 2 * N), np.float32)
+    for (r0, r1), part in zip(rows, parts):
+        U[r0:r1] = part[r0:r1]
+    O = np.triu(U) + np.triu(U, 1).T
+    for got, want in ((Mrr, O[:N, :N]), (Mrg, O[:N, N:]), (Mgg, O[N:, N:])):
+        assert np.abs(got - want).max() <= 1e-5 * want.max()
+        off = want > 0
+        assert (np.abs(got - want)[off] / want[off]).max() <= 1e-5
+    expect = om.scores_from_matrices(O[:N, :N], O[:N, N:], O[N:, N:])
+    for k in KEYS:
+        assert scores[k] == pytest.approx(expect[k], rel=1e-5, abs=1e-12), k
