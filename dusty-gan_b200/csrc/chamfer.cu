@@ -55,6 +55,7 @@ struct Params {
   int* idx1; int* idx2;
 };
 
+template <int NT>
 __device__ __forceinline__ double block_sum(double v, double* red) {
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -65,19 +66,24 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   double s = 0.0;
   if (threadIdx.x == 0) {
     #pragma unroll
-    for (int w = 0; w < TPB / 32; ++w) s += red[w];   // fixed order: result independent of sharding
+    for (int w = 0; w < NT / 32; ++w) s += red[w];   // fixed order: result independent of sharding
   }
   return s;
 }
 
-template <int R, bool MATRIX, bool MERGED>
-__global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
+// NT threads per CTA. The register tile of R = 8 rows per thread is what makes the search FMA-bound
+// (one LDS.128 pair feeds 24 FFMA2), so small clouds keep R = 8 and shrink the CTA instead: 2048 rows
+// -> 256 threads, 1024 -> 128, 512 -> 64, 256 -> 32 (the matrix front end's table, pick_shape). Every
+// shape keeps 16 warps of 128 registers per SM; the R < 8 instantiations (batch front end on small
+// batches, odd sizes) trade registers for residency because their CTAs are short.
+template <int R, bool MATRIX, bool MERGED, int NT = TPB>
+__global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* const tiles = reinterpret_cast<float4*>(smem_raw);
   __shared__ uint64_t bars[2];
-  __shared__ double red[TPB / 32];
+  __shared__ double red[NT / 32];
 
-  constexpr int RB = TPB * R;
+  constexpr int RB = NT * R;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
 
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
 // Merged clouds have arbitrary point counts, so the last row block of a direction is usually almost empty
 // (16 390 points = 8 full blocks + 6 rows). There a warp owns 32 R consecutive rows, and a warp without
 // live rows skips the search: the FMA pipe it would have occupied goes to the SM's other resident CTA.
-#define K_ROW(r) (MERGED ? rb * RB + (tid >> 5) * (32 * R) + (r) * 32 + lane : rb * RB + (r) * TPB + tid)
+#define K_ROW(r) (MERGED ? rb * RB + (tid >> 5) * (32 * R) + (r) * 32 + lane : rb * RB + (r) * NT + tid)
 #define K_countX (MERGED ? mx.x : p.countX)
 #define K_countY (MERGED ? my.x : p.countY)
 #define K_paddedX (MERGED ? (mx.x + CHUNK - 1) / CHUNK * CHUNK : p.paddedX)
@@ -119,6 +125,9 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
   else if (dir_only == 0) { pos_begin = rb_only * ntY; pos_end = pos_begin + ntY; }
   else { pos_begin = seg0 + rb_only * ntX; pos_end = pos_begin + ntX; }
 
+  // the two tile buffers are as large as the largest tile of this launch (launch_nn sizes the dynamic shared
+  // memory the same way): small clouds leave room for more resident CTAs to hide the per-entry prologue
+  const int tstride = (R >= 8 && NT == TPB) ? TILE : min(TILE, max(p.paddedX, p.paddedY));
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncthreads();
 
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     const int padded = dir == 0 ? K_paddedY : K_paddedX;
     const int npts = min(TILE, padded - t * TILE);
     mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u);
-    bulk_g2s(tiles + buf * TILE, src, (uint32_t)npts * 16u, &bars[buf]);
+    bulk_g2s(tiles + buf * tstride, src, (uint32_t)npts * 16u, &bars[buf]);
   };
   if (tid == 0) issue(pos_begin, 0);
 
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
     }
 
     mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
-    const float4* const tp = tiles + buf * TILE;
+    const float4* const tp = tiles + buf * tstride;
     const int nch = min(TILE, scanpadded - t * TILE) / CHUNK;
 
     if (!MERGED || rb * RB + (tid >> 5) * (32 * R) < rowcount) {      // warp-uniform
@@ -272,12 +281,12 @@ __global__ void __launch_bounds__(TPB, 2) nn_kernel(const Params p) {
         }
       }
     }
-    if (MATRIX && pos == seg0 - 1) { S0 = block_sum(dsum, red); dsum = 0.0; }
+    if (MATRIX && pos == seg0 - 1) { S0 = block_sum<NT>(dsum, red); dsum = 0.0; }
     __syncthreads();   // everyone is done with tiles[buf] before it is refilled
   }
 
   if (MATRIX) {
-    const double S1 = block_sum(dsum, red);
+    const double S1 = block_sum<NT>(dsum, red);
     if (tid == 0) {
       const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
       p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
@@ -399,17 +408,27 @@ static int pick_r(int maxcount) {
   return 1;
 }
 
-template <int R, bool MATRIX, bool MERGED>
+template <int R, bool MATRIX, bool MERGED, int NT = TPB>
 static int launch_nn(const Params& p, dim3 grid, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};   // per instantiation and device: the attribute is per context
   const int dev = current_device();
   if (!configured[dev]) {
-    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX, MERGED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured[dev] = true;
   }
-  nn_kernel<R, MATRIX, MERGED><<<grid, TPB, SMEM_BYTES, st>>>(p);
+  const int tile_pts = (R >= 8 && NT == TPB) ? TILE : std::min(TILE, std::max(p.paddedX, p.paddedY));
+  nn_kernel<R, MATRIX, MERGED, NT><<<grid, NT, 2 * (size_t)tile_pts * 16, st>>>(p);
   DUSTY_AFTER_LAUNCH("chamfer nn_kernel");
   return 0;
+}
+
+// Dense matrix front end: (threads per CTA, rows per thread) by cloud size, see nn_kernel.
+static int dispatch_matrix(int maxcount, const Params& p, dim3 grid, cudaStream_t st) {
+  if (maxcount > 1024) return launch_nn<8, true, false, 256>(p, grid, st);
+  if (maxcount > 512) return launch_nn<8, true, false, 128>(p, grid, st);
+  if (maxcount > 256) return launch_nn<8, true, false, 64>(p, grid, st);
+  if (maxcount > 128) return launch_nn<8, true, false, 32>(p, grid, st);
+  return launch_nn<4, true, false, 32>(p, grid, st);
 }
 
 template <bool MATRIX, bool MERGED>
@@ -571,5 +590,5 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
     p.idx1 = reinterpret_cast<int*>(ma); p.idx2 = reinterpret_cast<int*>(mb);
     return dispatch_nn<true, true>(pick_r(pa > pb ? pa : pb), p, grid, st);
   }
-  return dispatch_nn<true, false>(pick_r(pa > pb ? pa : pb), p, grid, st);
+  return dispatch_matrix(pa > pb ? pa : pb, p, grid, st);
 }
