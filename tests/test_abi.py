@@ -102,3 +102,23 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def _build_c_demo(tmp_path):
+    from dusty_gan_b200 import _lib
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(cuda, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"),
+                           "-L", libdir, "-ldustyb200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is C: the header parses as pedantic C99 and a program without Python or torch links
+    against the shared object (it runs in tests/test_gpu_c_abi.py)."""
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                           os.path.join(ROOT, "include", "dusty_b200.h")])
+    assert os.path.exists(_build_c_demo(tmp_path))
