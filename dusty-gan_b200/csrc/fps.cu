@@ -593,11 +593,14 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
   const float* const xyz = xyz_all + cloud * n * 3;
   int* const idx = idx_all + cloud * m;
   const int n128 = (n + BUCKET - 1) / BUCKET * BUCKET;
-  float* const cx = comp_all + cloud * 4 * n128;
-  float* const cy = cx + n128;
-  float* const cz = cy + n128;
-  int* const co = reinterpret_cast<int*>(cz + n128);
-  float* const ct = dist_all + cloud * n128;
+  // Bucket-major workspace: bucket k holds x[128] y[128] z[128] t[128] o[128] (2560 contiguous bytes), so one
+  // address plus immediates serves the four 128-bit loads and the store of an update (the planar layout
+  // cost ~20 instructions of 64-bit pointer arithmetic per touched bucket at this kernel's 40 registers).
+  // The comp (4 n128) and temp (n128) regions of the workspace are contiguous: 5 n128 floats per cloud.
+  (void)dist_all;
+  float* const cb = comp_all + cloud * 5 * n128;
+  auto at = [&](int e, int comp) -> float* { return cb + (e >> 7) * (5 * BUCKET) + comp * BUCKET + (e & (BUCKET - 1)); };
+  auto orig = [&](int e) -> int { return *reinterpret_cast<const int*>(at(e, 4)); };
   const float inf = __int_as_float(0x7f800000);
 
   int L = 0;
@@ -679,13 +682,13 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
       const float mag = fmaf(z, z, fmaf(x, x, y * y));
       if (!((double)mag <= 1e-3)) {
         const int e = atomicAdd(&cells[cell_of(x, y, z)], 1);
-        cx[e] = x; cy[e] = y; cz[e] = z; co[e] = k; ct[e] = 1e10f;
+        *at(e, 0) = x; *at(e, 1) = y; *at(e, 2) = z; *at(e, 3) = 1e10f; *reinterpret_cast<int*>(at(e, 4)) = k;
       }
     }
     const int E_pad = (E + BUCKET - 1) / BUCKET * BUCKET;
     if (tid < E_pad - E) {
       const int e = E + tid;
-      cx[e] = 0.f; cy[e] = 0.f; cz[e] = 0.f; co[e] = 0; ct[e] = -1.0f;
+      *at(e, 0) = 0.f; *at(e, 1) = 0.f; *at(e, 2) = 0.f; *at(e, 3) = -1.0f; *reinterpret_cast<int*>(at(e, 4)) = 0;
     }
     __threadfence_block();
     __syncthreads();                     // cell counters are dead: the region becomes boxes + records
@@ -694,9 +697,10 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
 
     for (int b = warp; b < nb; b += MT_NW) {
       const int e0 = b * BUCKET + 4 * lane;
-      const float4 px = *reinterpret_cast<const float4*>(cx + e0);
-      const float4 py = *reinterpret_cast<const float4*>(cy + e0);
-      const float4 pz = *reinterpret_cast<const float4*>(cz + e0);
+      const float* const pb = cb + b * (5 * BUCKET) + 4 * lane;
+      const float4 px = *reinterpret_cast<const float4*>(pb);
+      const float4 py = *reinterpret_cast<const float4*>(pb + BUCKET);
+      const float4 pz = *reinterpret_cast<const float4*>(pb + 2 * BUCKET);
       const float X[4] = {px.x, px.y, px.z, px.w}, Y[4] = {py.x, py.y, py.z, py.w}, Z[4] = {pz.x, pz.y, pz.z, pz.w};
       float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
       #pragma unroll
@@ -741,10 +745,11 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
       for (unsigned todo = need; todo != 0u; todo &= todo - 1u) {
         const int b = (__ffs(todo) - 1) * MT_NW + warp;
         const int e0 = b * BUCKET + 4 * lane;
-        const float4 px = *reinterpret_cast<const float4*>(cx + e0);
-        const float4 py = *reinterpret_cast<const float4*>(cy + e0);
-        const float4 pz = *reinterpret_cast<const float4*>(cz + e0);
-        const float4 t4 = *reinterpret_cast<const float4*>(ct + e0);
+        float* const pb = cb + b * (5 * BUCKET) + 4 * lane;
+        const float4 px = *reinterpret_cast<const float4*>(pb);
+        const float4 py = *reinterpret_cast<const float4*>(pb + BUCKET);
+        const float4 pz = *reinterpret_cast<const float4*>(pb + 2 * BUCKET);
+        const float4 t4 = *reinterpret_cast<const float4*>(pb + 3 * BUCKET);
         const f32x2 dx0 = sub2(pack2(px.x, px.y), c2x), dx1 = sub2(pack2(px.z, px.w), c2x);
         const f32x2 dy0 = sub2(pack2(py.x, py.y), c2y), dy1 = sub2(pack2(py.z, py.w), c2y);
         const f32x2 dz0 = sub2(pack2(pz.x, pz.y), c2z), dz1 = sub2(pack2(pz.z, pz.w), c2z);
@@ -754,7 +759,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
         unpack2(d0, d[0], d[1]);
         unpack2(d1, d[2], d[3]);
         float tq[4] = {fminf(d[0], t4.x), fminf(d[1], t4.y), fminf(d[2], t4.z), fminf(d[3], t4.w)};
-        *reinterpret_cast<float4*>(ct + e0) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+        *reinterpret_cast<float4*>(pb + 3 * BUCKET) = make_float4(tq[0], tq[1], tq[2], tq[3]);
         const float m4 = fmaxf(fmaxf(tq[0], tq[1]), fmaxf(tq[2], tq[3]));
         const unsigned vb = m4 < 0.f ? 0u : __float_as_uint(m4);
         const unsigned vmax = __reduce_max_sync(0xffffffffu, vb);
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
           #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (cm & (1u << q)) {
-              const unsigned key = tiekey(co[e0 + q]);
+              const unsigned key = tiekey(orig(e0 + q));
               if (key < lk) { lk = key; qb = q; }
             }
           }
@@ -792,7 +797,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
       const unsigned V = __reduce_max_sync(0xffffffffu, vb);
       unsigned cand = __ballot_sync(0xffffffffu, bvalid && vb == V);
       if ((cand & (cand - 1)) != 0u) {
-        const unsigned key = (bvalid && vb == V) ? tiekey(co[rec[bsafe].e]) : 0xffffffffu;
+        const unsigned key = (bvalid && vb == V) ? tiekey(orig(rec[bsafe].e)) : 0xffffffffu;
         const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
         cand = __ballot_sync(0xffffffffu, key == kmin);
       }
@@ -805,7 +810,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
       const unsigned VV = __reduce_max_sync(0xffffffffu, sv ? s2.val : 0u);
       unsigned cand2 = __ballot_sync(0xffffffffu, sv && s2.val == VV);
       if ((cand2 & (cand2 - 1)) != 0u) {
-        const unsigned key = (sv && s2.val == VV) ? tiekey(co[s2.e]) : 0xffffffffu;
+        const unsigned key = (sv && s2.val == VV) ? tiekey(orig(s2.e)) : 0xffffffffu;
         const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
         cand2 = __ballot_sync(0xffffffffu, key == kmin);
       }
@@ -818,7 +823,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
     }
     __threadfence_block();
     __syncthreads();
-    for (int j = 1 + tid; j < m; j += MT_TPB) idx[j] = co[j < MT_ELIST ? elist[j] : idx[j]];
+    for (int j = 1 + tid; j < m; j += MT_TPB) idx[j] = orig(j < MT_ELIST ? elist[j] : idx[j]);
   }
 
   if (out_all != nullptr) {
@@ -874,6 +879,8 @@ extern "C" int dusty_fps(const float* xyz, int b, int n, int m, int32_t* idx, fl
     return fail_arg(DUSTY_ENOSPACE, "fps: workspace %zu < %zu", workspace_bytes, dusty_fps_workspace_bytes(b, n, m));
   float* comp = static_cast<float*>(workspace);
   float* temp = reinterpret_cast<float*>(static_cast<char*>(workspace) + fps_comp_bytes(b, n));
+  // fps_multi_kernel addresses both regions as one (5 n128 floats per cloud): they must be contiguous
+  if (temp != comp + (size_t)b * 4 * ((n + 127) / 128 * 128)) return fail_arg(DUSTY_EINVAL, "fps: workspace regions are not contiguous");
   static bool configured[kMaxDevices] = {};
   static bool force_flat = false, force_single = false, force_multi = false;
   const int dev = current_device();
