@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   __shared__ double red[NT / 32];
 
   constexpr int RB = NT * R;
+  // candidates per search chunk = the window the exact pass re-evaluates per row and tile. Small clouds (the
+  // shrunken CTAs) take 16: the exact pass is a fixed cost per row, 14 % of the search at 512 points with 32.
+  constexpr int CH = NT < TPB ? CHUNK / 2 : CHUNK;
+  constexpr int PR = CH / 2;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
 
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
 
     mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
     const float4* const tp = tiles + buf * tstride;
-    const int nch = min(TILE, scanpadded - t * TILE) / CHUNK;
+    const int nch = min(TILE, scanpadded - t * TILE) / CH;
 
     if (!MERGED || rb * RB + (tid >> 5) * (32 * R) < rowcount) {      // warp-uniform
     // ---- search: which chunk of this tile holds the smallest |b|^2 - 2 a.b ----
@@ -187,10 +191,10 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
     #pragma unroll
     for (int r = 0; r < R; ++r) { cur[r] = __int_as_float(0x7f800000); cid[r] = 0; }
     for (int c = 0; c < nch; ++c) {
-      const float4* cp = tp + c * CHUNK;
+      const float4* cp = tp + c * CH;
       float cm[R];
       #pragma unroll
-      for (int k = 0; k < PAIRS; ++k) {
+      for (int k = 0; k < PR; ++k) {
         const float4 q0 = cp[2 * k], q1 = cp[2 * k + 1];
         const f32x2 bx = pack2(q0.x, q0.y), by = pack2(q0.z, q0.w);
         const f32x2 bz = pack2(q1.x, q1.y), bn = pack2(q1.z, q1.w);
@@ -226,11 +230,11 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
         eidx[r] = 0x7fffffff;
         const f32x2 mh = pack2(-0.5f, -0.5f);      // exact: recovers the row point from -2a
         ax2[r] = mul2(nax[g + r], mh); ay2[r] = mul2(nay[g + r], mh); az2[r] = mul2(naz[g + r], mh);
-        cp[r] = tp + cid[g + r] * CHUNK;
+        cp[r] = tp + cid[g + r] * CH;
       }
       #pragma unroll 4
-      for (int k = 0; k < PAIRS; ++k) {
-        const int kk = (k + lane) & (PAIRS - 1);   // lanes start on different banks
+      for (int k = 0; k < PR; ++k) {
+        const int kk = (k + lane) & (PR - 1);   // lanes start on different banks
         #pragma unroll
         for (int r = 0; r < G; ++r) {
           const float4 q0 = cp[r][2 * kk], q1 = cp[r][2 * kk + 1];
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           if (MATRIX) {
             e[r] = min3(e[r], lo, hi);
           } else {
-            const int i0 = t * TILE + cid[g + r] * CHUNK + 2 * kk;
+            const int i0 = t * TILE + cid[g + r] * CH + 2 * kk;
             if (lo < e[r] || (lo == e[r] && i0 < eidx[r])) { e[r] = lo; eidx[r] = i0; }
             if (hi < e[r] || (hi == e[r] && i0 + 1 < eidx[r])) { e[r] = hi; eidx[r] = i0 + 1; }
           }
