@@ -512,7 +512,9 @@ def main():
         # (DUSTY_MATRIX_MERGE_ORIGIN), so the executed pair count is data dependent: count it
         kept = torch.cat([(c != 0).any(-1).sum(1) + ((c == 0).all(-1).any(1)).long() for c in (ref, gen)]).double()
         exe_flops = 12.0 * float((kept.sum() ** 2 + (kept ** 2).sum()) / 2) / world
-        merged = {"points_scanned_mean": float(kept.mean()), "points_per_cloud": P}
+        merged = {"points_kept_mean": float(kept.mean()), "points_per_cloud": P,
+                  "note": "kept points are spatially sorted and chunks are pruned by box distance (exact): the executed pair count is "
+                          "data dependent and not counted by the kernel, so 'executed' below is an upper bound (every kept pair)"}
     peak_nominal = SM_COUNT * FP32_LANES * 2 * sm_max_mhz * 1e6 / 1e12
     sink = torch.zeros(1, device=device)
     import ctypes as C

@@ -82,6 +82,13 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   float4* const tiles = reinterpret_cast<float4*>(smem_raw);
   __shared__ uint64_t bars[2];
   __shared__ double red[NT / 32];
+  // merged + sorted clouds (prep_sort_kernel): per-chunk bounding boxes of the tile in flight (two buffers)
+  // and the box of each warp's rows; dist1 / dist2 carry the X / Y side box tables (null: no pruning)
+  __shared__ float4 sbox[MERGED ? 2 * 2 * (TILE / CHUNK) : 1];
+  __shared__ float4 wbox[MERGED ? 2 * (NT / 32) : 1];
+  const float4* const bxX = MERGED ? reinterpret_cast<const float4*>(p.dist1) : nullptr;
+  const float4* const bxY = MERGED ? reinterpret_cast<const float4*>(p.dist2) : nullptr;
+  const bool prune = MERGED && bxX != nullptr;
 
   constexpr int RB = NT * R;
   // candidates per search chunk = the window the exact pass re-evaluates per row and tile. Small clouds (the
@@ -135,13 +142,30 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncthreads();
 
+  // With pruning a row block starts on the tile at its own relative position in the (spatially sorted)
+  // other cloud, where its nearest neighbours most likely are: the bound it leaves prunes the other tiles.
+  auto tile_of = [&](int dir, int rb, int t) -> int {
+    if (!prune) return t;
+    const int nt = dir == 0 ? ntY : ntX, nrb = dir == 0 ? nrbX : nrbY;
+    return (t + rb * nt / nrb) % nt;
+  };
   // tile stream: position -> (direction, row block, scan tile)
   auto issue = [&](int pos, int buf) {
-    int dir, t;
-    if (pos < seg0) { dir = 0; t = pos % ntY; } else { dir = 1; t = (pos - seg0) % ntX; }
+    int dir, t, rb;
+    if (pos < seg0) { dir = 0; rb = pos / ntY; t = pos - rb * ntY; } else { dir = 1; const int q = pos - seg0; rb = q / ntX; t = q - rb * ntX; }
+    if (MERGED) t = tile_of(dir, rb, t);
     const float4* src = (dir == 0 ? sy : sx) + (long long)t * TILE;
     const int padded = dir == 0 ? K_paddedY : K_paddedX;
     const int npts = min(TILE, padded - t * TILE);
+    if (MERGED && prune) {
+      const float4* bsrc = (dir == 0 ? bxY + (long long)cj * (p.paddedY / CHUNK * 2) : bxX + (long long)ci * (p.paddedX / CHUNK * 2)) +
+                           t * (TILE / CHUNK * 2);
+      const uint32_t bbytes = (uint32_t)(npts / CHUNK) * 32u;
+      mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u + bbytes);
+      bulk_g2s(tiles + buf * tstride, src, (uint32_t)npts * 16u, &bars[buf]);
+      bulk_g2s(sbox + buf * (2 * (TILE / CHUNK)), bsrc, bbytes, &bars[buf]);
+      return;
+    }
     mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u);
     bulk_g2s(tiles + buf * tstride, src, (uint32_t)npts * 16u, &bars[buf]);
   };
@@ -178,19 +202,71 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
         eb[r] = __int_as_float(0x7f800000);
         ei[r] = 0;
       }
+      if (MERGED && prune) {            // bounding box of this warp's live rows (a = -0.5 * (-2a) exactly)
+        const float inf = __int_as_float(0x7f800000);
+        float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (K_ROW(r) < rowcount) {
+            float ax, ay, az, dummy;
+            unpack2(nax[r], ax, dummy); unpack2(nay[r], ay, dummy); unpack2(naz[r], az, dummy);
+            ax *= -0.5f; ay *= -0.5f; az *= -0.5f;
+            l0 = fminf(l0, ax); l1 = fminf(l1, ay); l2 = fminf(l2, az);
+            h0 = fmaxf(h0, ax); h1 = fmaxf(h1, ay); h2 = fmaxf(h2, az);
+          }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+          l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+          l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+        }
+        if (lane == 0) { wbox[2 * (tid >> 5)] = make_float4(l0, l1, l2, 0.f); wbox[2 * (tid >> 5) + 1] = make_float4(h0, h1, h2, 0.f); }
+        __syncwarp();
+      }
     }
 
     mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
     const float4* const tp = tiles + buf * tstride;
-    const int nch = min(TILE, scanpadded - t * TILE) / CH;
+    const int te = MERGED ? tile_of(dir, rb, t) : t;     // which tile of the scanned cloud this buffer holds
+    const int nch = min(TILE, scanpadded - te * TILE) / CH;
 
     if (!MERGED || rb * RB + (tid >> 5) * (32 * R) < rowcount) {      // warp-uniform
+    // ---- pruning (merged + sorted clouds): chunks whose box is no closer to the box of this warp's rows than
+    //      every current minimum of those rows cannot lower any of them. LB is the reference's distance formula
+    //      on the per-axis gaps: each of its operations is monotone in |dx|,|dy|,|dz| and so is rounding, hence
+    //      LB <= d(a,b) in floating point for every row a of the warp and candidate b of the chunk.
+    unsigned long long vmask = ~0ull;
+    if (MERGED && prune) {
+      float m = 0.0f;
+      #pragma unroll
+      for (int r = 0; r < R; ++r) if (K_ROW(r) < rowcount) m = fmaxf(m, eb[r]);
+      const float ubmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));   // distances are >= 0
+      const float4 rl = wbox[2 * (tid >> 5)], rh = wbox[2 * (tid >> 5) + 1];
+      const float4* const sb = sbox + buf * (2 * (TILE / CHUNK));
+      unsigned part[2];
+      #pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h * 32 + lane;
+        bool visit = false;
+        if (c < nch) {
+          const float4 bl = sb[2 * c], bh = sb[2 * c + 1];
+          const float gx = max3(0.0f, bl.x - rh.x, rl.x - bh.x);
+          const float gy = max3(0.0f, bl.y - rh.y, rl.y - bh.y);
+          const float gz = max3(0.0f, bl.z - rh.z, rl.z - bh.z);
+          visit = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))) < ubmax;
+        }
+        part[h] = __ballot_sync(0xffffffffu, visit);
+      }
+      vmask = (unsigned long long)part[0] | ((unsigned long long)part[1] << 32);
+    }
     // ---- search: which chunk of this tile holds the smallest |b|^2 - 2 a.b ----
     float cur[R];
     int cid[R];
     #pragma unroll
     for (int r = 0; r < R; ++r) { cur[r] = __int_as_float(0x7f800000); cid[r] = 0; }
     for (int c = 0; c < nch; ++c) {
+      if (MERGED && !((vmask >> c) & 1ull)) continue;      // warp-uniform
       const float4* cp = tp + c * CH;
       float cm[R];
       #pragma unroll
@@ -218,6 +294,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
 
     // ---- exact: re-evaluate the winning chunk with the reference's rounding ----
     constexpr int G = R < 4 ? R : 4;
+    if (!MERGED || vmask != 0ull)         // nothing scanned in this tile: nothing to re-evaluate
     #pragma unroll
     for (int g = 0; g < R; g += G) {
       float e[G];
@@ -377,6 +454,133 @@ __global__ void __launch_bounds__(256) prep_merge_kernel(const float* __restrict
   for (int i = kept + tid; i < padded; i += 256) put(i, nan, nan, nan, nan);
 }
 
+// Merged origins + spatial order (clouds of at most SORT_CAP points): the kept points are sorted by a
+// Morton cell key (x, y interleaved at 7 bits each, z 1 bit, ties by original index, so the order is
+// deterministic) with a bitonic network in shared memory, written in scan format, and every 32-candidate
+// chunk gets its bounding box. The matrix kernel then skips a chunk whenever the gap between the chunk's
+// box and the box of a warp's 256 rows is already no smaller than every current minimum of those rows:
+// exact, because every operation of the distance is monotone in |dx|,|dy|,|dz| and so is rounding.
+constexpr int SORT_CAP = 32768;
+constexpr int SORT_TPB = 1024;
+
+__device__ __forceinline__ unsigned spread7(unsigned v) {          // abcdefg -> a0b0c0d0e0f0g
+  v &= 0x7fu;
+  v = (v | (v << 4)) & 0x070fu;
+  v = (v | (v << 2)) & 0x1333u;
+  v = (v | (v << 1)) & 0x1555u;
+  return v;
+}
+
+__global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __restrict__ xyz, int count, long long stride,
+                                                             float4* __restrict__ out, int2* __restrict__ meta,
+                                                             float4* __restrict__ boxes, int boxstride) {
+  extern __shared__ unsigned keys[];            // n2 keys (next power of two >= count)
+  __shared__ float red[SORT_TPB / 32][6];
+  __shared__ int wsum[SORT_TPB / 32];
+  const long long c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* src = xyz + c * count * 3;
+  float* dst = reinterpret_cast<float*>(out + c * stride);
+  float4* bdst = boxes + c * boxstride;
+  const float inf = __int_as_float(0x7f800000);
+  int n2 = 1;
+  while (n2 < count) n2 <<= 1;
+
+  // ---- bounding box of the non-zero points, their number ----
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  int mine = 0;
+  for (int i = tid; i < count; i += SORT_TPB) {
+    const float x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+    if (x != 0.0f || y != 0.0f || z != 0.0f) {
+      ++mine;
+      lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+      hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+    }
+  }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  }
+  if (lane == 0) {
+    wsum[warp] = mine;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) { red[warp][a] = lo[a]; red[warp][3 + a] = hi[a]; }
+  }
+  __syncthreads();
+  int total = 0;
+  for (int w = 0; w < SORT_TPB / 32; ++w) {
+    total += wsum[w];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], red[w][a]); hi[a] = fmaxf(hi[a], red[w][3 + a]); }
+  }
+  const float sxs = hi[0] > lo[0] ? 128.0f / (hi[0] - lo[0]) : 0.0f;
+  const float sys = hi[1] > lo[1] ? 128.0f / (hi[1] - lo[1]) : 0.0f;
+  const float szs = hi[2] > lo[2] ? 2.0f / (hi[2] - lo[2]) : 0.0f;
+
+  // ---- keys: (cell << 15) | original index; zero points and padding sort to the end ----
+  for (int i = tid; i < n2; i += SORT_TPB) {
+    unsigned key = 0xffffffffu;
+    if (i < count) {
+      const float x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+      if (x != 0.0f || y != 0.0f || z != 0.0f) {
+        const unsigned ix = (unsigned)min(127, max(0, (int)((x - lo[0]) * sxs)));
+        const unsigned iy = (unsigned)min(127, max(0, (int)((y - lo[1]) * sys)));
+        const unsigned iz = (unsigned)min(1, max(0, (int)((z - lo[2]) * szs)));
+        key = ((((spread7(ix) | (spread7(iy) << 1)) << 1) | iz) << 15) | (unsigned)i;
+      }
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (n2 >> 1); t += SORT_TPB) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned a = keys[i], b = keys[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- sorted points in scan format + one origin point + NaN padding; a box per 32-candidate chunk ----
+  const int zeros = count - total;
+  const int kept = total + (zeros > 0 ? 1 : 0);
+  const int padded = (kept + CHUNK - 1) / CHUNK * CHUNK;
+  const float nan = __int_as_float(0x7fc00000);
+  for (int chunk = warp; chunk < padded / CHUNK; chunk += SORT_TPB / 32) {
+    const int pos = chunk * CHUNK + lane;
+    float x = nan, y = nan, z = nan, n = nan;
+    if (pos < total) {
+      const int i = (int)(keys[pos] & 0x7fffu);
+      x = src[3 * i]; y = src[3 * i + 1]; z = src[3 * i + 2];
+      n = fmaf(z, z, fmaf(x, x, y * y));
+    } else if (pos == total && zeros > 0) {
+      x = y = z = n = 0.0f;
+    }
+    float* q = dst + (size_t)(pos >> 1) * 8 + (pos & 1);     // {x0,x1,y0,y1}{z0,z1,n0,n1}
+    q[0] = x; q[2] = y; q[4] = z; q[6] = n;
+    const bool real = pos < kept;
+    float l0 = real ? x : inf, l1 = real ? y : inf, l2 = real ? z : inf;
+    float h0 = real ? x : -inf, h1 = real ? y : -inf, h2 = real ? z : -inf;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+      l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+      l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+    }
+    if (lane == 0) { bdst[2 * chunk] = make_float4(l0, l1, l2, 0.f); bdst[2 * chunk + 1] = make_float4(h0, h1, h2, 0.f); }
+  }
+  if (tid == 0) meta[c] = make_int2(kept, zeros > 0 ? zeros : 1);
+}
+
 // Reference ChamferDistanceGradKernel (chamfer_distance.cu:148-172): own-term stores plus
 // scatter-adds through the arg-min indices.
 __global__ void __launch_bounds__(256) grad_kernel(int b, int n, const float* __restrict__ xyz1, int m,
@@ -463,6 +667,24 @@ static int run_prep_merge(const float* xyz, long long clouds, int count, float4*
   return 0;
 }
 
+static size_t box_bytes(long long clouds, int count) { return align_up((size_t)clouds * (padded_of(count) / CHUNK) * 32, 256); }
+
+static int run_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st) {
+  if (clouds == 0) return 0;
+  int n2 = 1;
+  while (n2 < count) n2 <<= 1;
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    DUSTY_CUDA(cudaFuncSetAttribute(prep_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 4));
+    configured[dev] = true;
+  }
+  prep_sort_kernel<<<(unsigned)clouds, SORT_TPB, (size_t)n2 * 4, st>>>(xyz, count, padded_of(count), out, meta, boxes,
+                                                                        padded_of(count) / CHUNK * 2);
+  DUSTY_AFTER_LAUNCH("chamfer prep_sort_kernel");
+  return 0;
+}
+
 }  // namespace chamfer
 }  // namespace dusty
 
@@ -540,8 +762,8 @@ extern "C" int dusty_chamfer_backward(const float* xyz1, const float* xyz2, int 
 
 extern "C" size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, int pb) {
   size_t s = 0;
-  if (na > 0 && pa > 0) s += align_up(scan_bytes(na, pa), 256) + meta_bytes(na);
-  if (nb > 0 && pb > 0) s += align_up(scan_bytes(nb, pb), 256) + meta_bytes(nb);
+  if (na > 0 && pa > 0) s += align_up(scan_bytes(na, pa), 256) + meta_bytes(na) + box_bytes(na, pa);
+  if (nb > 0 && pb > 0) s += align_up(scan_bytes(nb, pb), 256) + meta_bytes(nb) + box_bytes(nb, pb);
   return s;
 }
 
@@ -563,15 +785,24 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   if (!aligned16(workspace)) return fail_arg(DUSTY_EALIGN, "chamfer_matrix: workspace must be 16-byte aligned");
   const size_t need = dusty_chamfer_matrix_workspace_bytes(na, pa, symmetric ? 0 : nb, pb);
   if (workspace_bytes < need) return fail_arg(DUSTY_ENOSPACE, "chamfer_matrix: workspace %zu < %zu", workspace_bytes, need);
-  // workspace: [scan A][meta A]([scan B][meta B])
+  // workspace: [scan A][meta A][boxes A]([scan B][meta B][boxes B])
   char* const wsp = static_cast<char*>(workspace);
   float4* sa = reinterpret_cast<float4*>(wsp);
   int2* ma = reinterpret_cast<int2*>(wsp + align_up(scan_bytes(na, pa), 256));
-  char* const wsb = wsp + align_up(scan_bytes(na, pa), 256) + meta_bytes(na);
+  float4* ba = reinterpret_cast<float4*>(wsp + align_up(scan_bytes(na, pa), 256) + meta_bytes(na));
+  char* const wsb = wsp + align_up(scan_bytes(na, pa), 256) + meta_bytes(na) + box_bytes(na, pa);
   float4* sb = symmetric ? sa : reinterpret_cast<float4*>(wsb);
   int2* mb = symmetric ? ma : reinterpret_cast<int2*>(wsb + align_up(scan_bytes(nb, pb), 256));
+  float4* bb = symmetric ? ba : reinterpret_cast<float4*>(wsb + align_up(scan_bytes(nb, pb), 256) + meta_bytes(nb));
+  // merged clouds that fit the shared-memory sort are also put in spatial order with a box per chunk, and the
+  // kernel prunes chunks by box distance (DUSTY_CHAMFER_PRUNE=0 keeps the plain merged scan for A/B runs)
+  static const bool prune_enabled = [] { const char* e = getenv("DUSTY_CHAMFER_PRUNE"); return !(e && e[0] == '0'); }();
+  const bool sorted = merge && prune_enabled && pa <= SORT_CAP && pb <= SORT_CAP && pick_r(pa > pb ? pa : pb) == 8;
   if (!prepared) {
-    if (merge) {
+    if (sorted) {
+      if (int rc = run_prep_sort(A, na, pa, sa, ma, ba, st)) return rc;
+      if (!symmetric) if (int rc = run_prep_sort(B, nb, pb, sb, mb, bb, st)) return rc;
+    } else if (merge) {
       if (int rc = run_prep_merge(A, na, pa, sa, ma, st)) return rc;
       if (!symmetric) if (int rc = run_prep_merge(B, nb, pb, sb, mb, st)) return rc;
     } else {
@@ -592,6 +823,7 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   const dim3 grid(nb, rows, 1);
   if (merge) {
     p.idx1 = reinterpret_cast<int*>(ma); p.idx2 = reinterpret_cast<int*>(mb);
+    if (sorted) { p.dist1 = reinterpret_cast<float*>(ba); p.dist2 = reinterpret_cast<float*>(bb); }
     return dispatch_nn<true, true>(pick_r(pa > pb ? pa : pb), p, grid, st);
   }
   return dispatch_matrix(pa > pb ? pa : pb, p, grid, st);
