@@ -48,7 +48,7 @@ from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix  # noqa: E4
 scans = (torch.randn(2, 8, 96, 4, device="cuda") * 20) * (torch.rand(2, 8, 96, 1, device="cuda") > 0.3)
 preprocess_scans(scans, (8, 24), want=("xyz", "depth", "mask", "inv", "points"))
 preprocess_scans(scans[..., :3].contiguous(), (8, 96))
-u = torch.from_numpy(lidar_like_clouds(3, 2300, 6, dropped=0.5)).cuda()
+u = torch.from_numpy(lidar_like_clouds(3, 4200, 6, dropped=0.5)).cuda()       # > 1024 kept points: sorted + pruned path
 u[1] = 0
 print(chamfer_matrix(u, merge_origin=True))
 print(chamfer_matrix(u, u[:2, :600].contiguous(), merge_origin=True))
