@@ -151,9 +151,14 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   };
   // tile stream: position -> (direction, row block, scan tile)
   auto issue = [&](int pos, int buf) {
-    int dir, t, rb;
-    if (pos < seg0) { dir = 0; rb = pos / ntY; t = pos - rb * ntY; } else { dir = 1; const int q = pos - seg0; rb = q / ntX; t = q - rb * ntX; }
-    if (MERGED) t = tile_of(dir, rb, t);
+    int dir, t;
+    if (!MERGED) {
+      if (pos < seg0) { dir = 0; t = pos % ntY; } else { dir = 1; t = (pos - seg0) % ntX; }
+    } else {
+      int rb;
+      if (pos < seg0) { dir = 0; rb = pos / ntY; t = pos - rb * ntY; } else { dir = 1; const int q = pos - seg0; rb = q / ntX; t = q - rb * ntX; }
+      t = tile_of(dir, rb, t);
+    }
     const float4* src = (dir == 0 ? sy : sx) + (long long)t * TILE;
     const int padded = dir == 0 ? K_paddedY : K_paddedX;
     const int npts = min(TILE, padded - t * TILE);
