@@ -55,6 +55,7 @@ for d in kernels:
     key = ("chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0>" in name or "nn_kernel<8, 1>" in name
            else "chamfer_nn_kernel_merged_24x32768" if "nn_kernel" in name
            else "head_project_dusty1_b256" if "head_project" in name
+           else "chamfer_prep_sort_24x32768" if "prep_sort" in name
            else "scan_preprocess_256x64x2048" if "scan_preprocess" in name
            else "fps_multi_888clouds" if "fps_multi" in name else "fps_pruned_148clouds")
     traffic[key] = to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"])
