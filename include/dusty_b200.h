@@ -117,7 +117,11 @@ DUSTY_API size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, in
  *                                points of a cloud are scanned as ONE point of that multiplicity:
  *                                the minima are unchanged (duplicate candidates never change a
  *                                minimum, identical rows share theirs) and the means still divide
- *                                by pa / pb, so M is the same matrix for a fraction of the work. */
+ *                                by pa / pb, so M is the same matrix for a fraction of the work.
+ *                                Clouds of at most 32768 points are also put in spatial (Morton) order
+ *                                with a bounding box per 32 points, and the kernel skips candidate
+ *                                chunks whose box is no closer to a warp's rows than their current
+ *                                minima -- exact, the bound is evaluated in the kernel's own rounding. */
 #define DUSTY_MATRIX_SYMMETRIC    1
 #define DUSTY_MATRIX_MIRROR       2
 #define DUSTY_MATRIX_COMPACT_ROWS 4
