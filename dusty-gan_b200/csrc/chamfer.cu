@@ -802,7 +802,15 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   // merged clouds that fit the shared-memory sort are also put in spatial order with a box per chunk, and the
   // kernel prunes chunks by box distance (DUSTY_CHAMFER_PRUNE=0 keeps the plain merged scan for A/B runs)
   static const bool prune_enabled = [] { const char* e = getenv("DUSTY_CHAMFER_PRUNE"); return !(e && e[0] == '0'); }();
-  const bool sorted = merge && prune_enabled && pa <= SORT_CAP && pb <= SORT_CAP && pick_r(pa > pb ? pa : pb) == 8;
+  int merged_r = pick_r(pa > pb ? pa : pb);
+  const bool sorted = merge && prune_enabled && pa <= SORT_CAP && pb <= SORT_CAP && merged_r == 8;
+  if (sorted) {
+    // Pruning works per warp, and a warp owns 32 R consecutive sorted rows: fewer rows per thread give tighter row
+    // boxes (more chunks skipped) against fewer FFMA2 per LDS. Measured on the bench's un-sampled clouds, entries/s
+    // per GPU: R = 8 46.3 k, R = 4 61.0 k, R = 2 57.8 k, R = 1 39.0 k. DUSTY_CHAMFER_MERGED_R re-creates the A/B.
+    merged_r = 4;
+    if (const char* e = getenv("DUSTY_CHAMFER_MERGED_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) merged_r = v; }
+  }
   if (!prepared) {
     if (sorted) {
       if (int rc = run_prep_sort(A, na, pa, sa, ma, ba, st)) return rc;
@@ -829,7 +837,7 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   if (merge) {
     p.idx1 = reinterpret_cast<int*>(ma); p.idx2 = reinterpret_cast<int*>(mb);
     if (sorted) { p.dist1 = reinterpret_cast<float*>(ba); p.dist2 = reinterpret_cast<float*>(bb); }
-    return dispatch_nn<true, true>(pick_r(pa > pb ? pa : pb), p, grid, st);
+    return dispatch_nn<true, true>(merged_r, p, grid, st);
   }
   return dispatch_matrix(pa > pb ? pa : pb, p, grid, st);
 }
