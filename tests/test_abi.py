@@ -122,3 +122,27 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
                            os.path.join(ROOT, "include", "dusty_b200.h")])
     assert os.path.exists(_build_c_demo(tmp_path))
+
+
+def test_hot_kernels_keep_their_occupancy_shape():
+    """Register budgets the measured numbers depend on (cuobjdump -res-usage): the dense Chamfer kernel at 128
+    registers without local memory (two CTAs of 256 threads per SM), the head kernel at 32 (2048 threads per SM),
+    the six-clouds-per-SM FPS kernel at 40, and no stack or local memory in any of them."""
+    from dusty_gan_b200 import _lib
+    out = subprocess.check_output(["cuobjdump", "-res-usage", _lib.LIB_PATH], text=True)
+    usage = dict(re.findall(r"Function (\S+):\s+REG:(\d+) STACK:\d+ SHARED:\d+ LOCAL:\d+", out))
+    local = dict(re.findall(r"Function (\S+):\s+REG:\d+ STACK:(\d+) SHARED:\d+ LOCAL:\d+", out))
+
+    def one(fragment):
+        names = [n for n in usage if fragment in n]
+        assert len(names) == 1, (fragment, names)
+        return names[0]
+    dense = one("nn_kernelILi8ELb1ELb0ELi256")
+    assert int(usage[dense]) <= 128 and int(local[dense]) == 0
+    for frag in ("nn_kernelILi8ELb1ELb0ELi128", "nn_kernelILi8ELb1ELb0ELi64", "nn_kernelILi8ELb1ELb0ELi32", "nn_kernelILi4ELb1ELb1ELi256"):
+        n = one(frag)
+        assert int(usage[n]) <= 128 and int(local[n]) == 0, frag
+    assert int(usage[one("head_project_kernelILi1ELb0ELi1")]) <= 32
+    assert int(usage[one("head_project_kernelILi2ELb0ELi1")]) <= 40      # DUSty-II: 36 registers, 7 CTAs per SM
+    assert int(usage[one("fps_multi_kernel")]) <= 40
+    assert int(usage[one("scan_preprocess_kernel")]) <= 40
