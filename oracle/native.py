@@ -103,3 +103,14 @@ def downsample_point_clouds(xyz, k):
     a = _f(xyz)
     idx = fps(a, k)
     return np.take_along_axis(a, idx[:, :, None].astype(np.int64), axis=1), idx
+
+
+def box_bound_violations(rows, cands):
+    """(number of (row, candidate) pairs whose reference-rounded distance is below the kernels' box lower bound,
+    the bound itself). The pruning in csrc/fps.cu and csrc/chamfer.cu is exact iff the count is always 0."""
+    a, c = _f(rows).reshape(-1, 3), _f(cands).reshape(-1, 3)
+    fn = lib().oracle_box_bound_violations
+    fn.restype = C.c_longlong
+    lb = C.c_float()
+    bad = fn(C.c_int(len(a)), _p(a), C.c_int(len(c)), _p(c), C.byref(lb))
+    return int(bad), float(lb.value)

@@ -210,3 +210,29 @@ def test_nearest_index_is_torchs():
         src = torch.arange(n_in, dtype=torch.float32)[None, None, None]
         want = F.interpolate(src, size=(1, n_out), mode="nearest")[0, 0, 0].long().numpy()
         assert np.array_equal(rd.nearest_index(n_out, n_in), want), (n_in, n_out)
+
+
+def test_box_lower_bound_never_exceeds_a_reference_rounded_distance():
+    """The exactness argument of both pruned kernels (FPS buckets, Chamfer chunks on merged clouds): the bound
+    formed on the per-axis gaps between two bounding boxes, in the reference's own fma pattern, is <= the
+    reference-rounded distance of EVERY pair drawn from the two boxes -- including touching and overlapping
+    boxes, gaps of a few ulp, huge and denormal coordinates, and a single centre point against a box (FPS)."""
+    rng = np.random.default_rng(123)
+    total_pairs = 0
+    for trial in range(400):
+        na = int(rng.choice([1, 1, 7, 32, 256])); nb = int(rng.choice([1, 32, 128]))
+        scale = float(rng.choice([1e-30, 1e-6, 1e-2, 1.0, 1e3, 1e15]))
+        a = rng.standard_normal((na, 3)).astype(np.float32) * np.float32(scale * rng.uniform(0.01, 1))
+        shift = rng.standard_normal(3) * scale * rng.choice([0.0, 1e-7, 1e-3, 1.0, 10.0])
+        c = (rng.standard_normal((nb, 3)) * scale * rng.uniform(0.01, 1) + shift).astype(np.float32)
+        if trial % 5 == 0:          # boxes that touch within an ulp along one axis
+            c[:, 0] = np.nextafter(a[:, 0].max(), np.float32(np.inf), dtype=np.float32) + np.abs(c[:, 0] - c[:, 0].min())
+        bad, lb = native.box_bound_violations(a, c)
+        assert bad == 0, (trial, na, nb, scale, lb)
+        assert lb >= 0.0
+        total_pairs += na * nb
+    assert total_pairs > 500_000
+    # sanity of the checker itself: disjoint unit cubes one apart along x have LB = 1 exactly
+    a = rng.uniform(0, 1, (50, 3)).astype(np.float32); c = rng.uniform(0, 1, (50, 3)).astype(np.float32) + np.float32([2, 0, 0])
+    a[0] = (1, 0, 0); c[0] = (2, 0, 0)
+    assert native.box_bound_violations(a, c) == (0, 1.0)
