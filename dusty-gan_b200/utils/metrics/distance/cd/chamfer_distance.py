@@ -1,52 +1,60 @@
-"""Chamfer distance on libdustyb200 (mirror of reference
-utils/metrics/distance/cd/chamfer_distance.py:16-69)."""
+"""Chamfer distance on libdustyb200.
+
+Public names and call signatures are those of the reference module
+(utils/metrics/distance/cd/chamfer_distance.py:16-69): ``ChamferDistanceFunction``, ``ChamferDistance`` and the
+callable ``chamfer_distance(xyz1, xyz2) -> (dist1, dist2)`` with a backward pass. The body is two C-ABI calls.
+"""
 import torch
 
 from ..... import _lib
 
 
+def _nn_both_ways(a, b):
+    """a (B,N,3), b (B,M,3) contiguous CUDA f32 -> squared NN distances and arg-mins in both directions."""
+    B, N, M = a.size(0), a.size(1), b.size(1)
+    opts = dict(device=a.device)
+    d_ab = torch.empty(B, N, dtype=torch.float32, **opts)
+    d_ba = torch.empty(B, M, dtype=torch.float32, **opts)
+    i_ab = torch.empty(B, N, dtype=torch.int32, **opts)
+    i_ba = torch.empty(B, M, dtype=torch.int32, **opts)
+    lib = _lib.load()
+    ws_bytes = lib.dusty_chamfer_forward_workspace_bytes(B, N, M)
+    ws = _lib.workspace(ws_bytes, a.device)
+    with torch.cuda.device(a.device):      # the reference launches on whatever device is current
+        rc = lib.dusty_chamfer_forward(_lib.ptr(a), _lib.ptr(b), B, N, M, _lib.ptr(d_ab), _lib.ptr(d_ba), _lib.ptr(i_ab),
+                                       _lib.ptr(i_ba), _lib.ptr(ws), ws_bytes, _lib.stream_of(a))
+    _lib.check(rc, "dusty_chamfer_forward")
+    return d_ab, d_ba, i_ab, i_ba
+
+
+def _scatter_grads(a, b, g_ab, g_ba, i_ab, i_ba):
+    """Gradients of sum(g_ab * d_ab) + sum(g_ba * d_ba) with respect to both clouds (reference .cu:148-190)."""
+    ga, gb = torch.empty_like(a), torch.empty_like(b)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.dusty_chamfer_backward(_lib.ptr(a), _lib.ptr(b), a.size(0), a.size(1), b.size(1), _lib.ptr(g_ab), _lib.ptr(g_ba),
+                                        _lib.ptr(i_ab), _lib.ptr(i_ba), _lib.ptr(ga), _lib.ptr(gb), None, 0, _lib.stream_of(a))
+    _lib.check(rc, "dusty_chamfer_backward")
+    return ga, gb
+
+
 class ChamferDistanceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        _lib.require_cuda(xyz1, "xyz1")
-        _lib.require_cuda(xyz2, "xyz2")
-        if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.size(2) != 3 or xyz2.size(2) != 3 or xyz1.size(0) != xyz2.size(0):
+        for t, name in ((xyz1, "xyz1"), (xyz2, "xyz2")):
+            _lib.require_cuda(t, name)
+        ok = xyz1.dim() == 3 and xyz2.dim() == 3 and xyz1.size(2) == 3 and xyz2.size(2) == 3 and xyz1.size(0) == xyz2.size(0)
+        if not ok:
             raise ValueError(f"expected (B,N,3) and (B,M,3), got {tuple(xyz1.shape)} and {tuple(xyz2.shape)}")
-        batchsize, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-        device = xyz1.device
-        xyz1 = xyz1.contiguous()
-        xyz2 = xyz2.contiguous()
-        dist1 = torch.empty(batchsize, n, device=device)
-        dist2 = torch.empty(batchsize, m, device=device)
-        idx1 = torch.empty(batchsize, n, dtype=torch.int, device=device)
-        idx2 = torch.empty(batchsize, m, dtype=torch.int, device=device)
-        lib = _lib.load()
-        nbytes = lib.dusty_chamfer_forward_workspace_bytes(batchsize, n, m)
-        ws = _lib.workspace(nbytes, device)
-        with torch.cuda.device(device):
-            _lib.check(lib.dusty_chamfer_forward(_lib.ptr(xyz1), _lib.ptr(xyz2), batchsize, n, m, _lib.ptr(dist1),
-                                                 _lib.ptr(dist2), _lib.ptr(idx1), _lib.ptr(idx2), _lib.ptr(ws), nbytes,
-                                                 _lib.stream_of(xyz1)), "dusty_chamfer_forward")
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
-        return dist1, dist2
+        a, b = xyz1.contiguous(), xyz2.contiguous()
+        d_ab, d_ba, i_ab, i_ba = _nn_both_ways(a, b)
+        ctx.save_for_backward(a, b, i_ab, i_ba)
+        return d_ab, d_ba
 
     @staticmethod
-    def backward(ctx, graddist1, graddist2):
-        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        graddist1 = graddist1.contiguous()
-        graddist2 = graddist2.contiguous()
-        b, n, _ = xyz1.shape
-        m = xyz2.size(1)
-        gradxyz1 = torch.empty_like(xyz1)
-        gradxyz2 = torch.empty_like(xyz2)
-        lib = _lib.load()
-        with torch.cuda.device(xyz1.device):
-            _lib.check(lib.dusty_chamfer_backward(_lib.ptr(xyz1), _lib.ptr(xyz2), b, n, m, _lib.ptr(graddist1),
-                                                  _lib.ptr(graddist2), _lib.ptr(idx1), _lib.ptr(idx2),
-                                                  _lib.ptr(gradxyz1), _lib.ptr(gradxyz2), None, 0,
-                                                  _lib.stream_of(xyz1)), "dusty_chamfer_backward")
-        return gradxyz1, gradxyz2
+    def backward(ctx, grad_ab, grad_ba):
+        a, b, i_ab, i_ba = ctx.saved_tensors
+        return _scatter_grads(a, b, grad_ab.contiguous(), grad_ba.contiguous(), i_ab, i_ba)
 
 
 class ChamferDistance(torch.nn.Module):
