@@ -38,6 +38,7 @@ class ScanParams(C.Structure):
                 ("disp_lo", C.c_float), ("inv_disp_range", C.c_float), ("drop_const", C.c_float)]
 
 
+ABI_VERSION = 2          # DUSTY_B200_ABI_VERSION of include/dusty_b200.h
 NOISE_NONE, NOISE_LOGISTIC, NOISE_UNIFORM = 0, 1, 2
 MATRIX_SYMMETRIC, MATRIX_MIRROR, MATRIX_COMPACT_ROWS, MATRIX_PREPARED, MATRIX_MERGE_ORIGIN = 1, 2, 4, 8, 16
 
@@ -56,6 +57,14 @@ SIGNATURES = {
     "dusty_chamfer_matrix": (C.c_int, [c_float_p, C.c_int, C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, c_float_p, C.c_longlong, C.c_void_p, C.c_size_t,
                                        C.c_void_p]),
+    "dusty_nn_keys_bytes": (C.c_size_t, [C.c_int]),
+    "dusty_nn_keys_reset": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dusty_chamfer_matrix_fused": (C.c_int, [c_float_p, C.c_int, C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, c_float_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dusty_cov_mmd_1nna_from_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p, C.c_size_t,
+                                               C.c_void_p]),
+    "dusty_symmetric_from_shards": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, C.c_longlong, C.c_void_p]),
     "dusty_cov_mmd_1nna_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "dusty_cov_mmd_1nna_finalize": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, c_float_p,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -97,7 +106,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dusty_abi_version() != 1:
+    if lib.dusty_abi_version() != ABI_VERSION:
         raise RuntimeError("libdustyb200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -18,10 +18,15 @@
 //            32-candidate chunk one compare/select that remembers which chunk holds the minimum;
 //   exact :  the winning chunk (1.6 % of the tile) is re-evaluated in the reference's rounding,
 //            d = fma(dz,dz,fma(dx,dx,dy*dy)) on differences, and the minimum of those is the
-//            result. Every reported distance is therefore a value the reference kernel would have
-//            computed for some candidate, and it is the reference's minimum unless two candidates
-//            in different chunks are closer to each other than the search's rounding error
-//            (~2^-23 (|a|^2+|b|^2)), in which case it exceeds the minimum by at most that much.
+//            result;
+//   guard :  the search also keeps the runner-up chunk's minimum. Whenever it lies within
+//            delta = 48 u (|a|^2 + D), u = 2^-24, D = the search's own estimate of the distance, of the
+//            winner's -- a rigorous bound on (search rounding error of two candidates) + (rounding of the
+//            reference formula), derived at search_window() -- the search cannot tell which chunk holds
+//            the reference's minimum, and the warp re-evaluates the WHOLE tile for that row in the
+//            reference's rounding (32 lanes x 64 candidates, two shuffles). Hence every distance (and
+//            index) returned is exactly the reference kernel's, for any finite input; the guard fires for
+//            ~0.1 % of the (row, tile) pairs on LiDAR-like clouds and costs < 0.5 %.
 #include <algorithm>
 #include <cstdlib>
 
@@ -53,6 +58,11 @@ struct Params {
   // int2 {points kept, weight of the last kept point} tables of the X / Y side: the struct keeps the
   // size the dense kernel was tuned with (two more parameter words changed ptxas' register allocation)
   int* idx1; int* idx2;
+  // fused MMD/COV/1-NNA epilogue (matrix front end; null: off). keys = 3 arrays of n_total packed
+  // (float bits << 32 | stacked index) minima: [0] leave-one-out nearest neighbour of every stacked cloud,
+  // [1] nearest reference cloud of every generated cloud, [2] nearest generated cloud of every reference cloud
+  unsigned long long* keys;
+  int n_total, n_ref, offX, offY;
 };
 
 template <int NT>
@@ -69,6 +79,48 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     for (int w = 0; w < NT / 32; ++w) s += red[w];   // fixed order: result independent of sharding
   }
   return s;
+}
+
+// Half-width of the search's blind spot around its own minimum `cur` for a row point a (see the header):
+// any candidate the reference kernel could prefer has a search value below cur + window. With u = 2^-24,
+// r^2 = D the squared distance of a candidate b, |b| <= |a| + r:
+//   search value s~ = fl chain of |b|^2 - 2 a.b: |s~ - s| <= u (6 |b|^2 + 6 |a||b|) <= u (21 |a|^2 + 15 D)
+//   reference value d~ = fma(dz,dz,fma(dx,dx,dy*dy)) on rounded differences: |d~ - D| <= 5 u D
+// so for the search's winner b^ and the reference's arg-min b* (d~(b*) <= d~(b^) => D(b*) <= (1 + 10u) D(b^)):
+//   s~(b*) - s~(b^) <= u (42 |a|^2 + 40 D(b^)),  D(b^) <= (cur + |a|^2)(1 + O(u)).
+// 48 u leaves > 12 % for the rounding of this very expression and of the comparison; 1e-36 covers underflow.
+__device__ __forceinline__ float search_window(float ax, float ay, float az, float cur) {
+  const float an = fmaf(az, az, fmaf(ax, ax, ay * ay));
+  return fmaf(2.86102295e-6f /* 48 * 2^-24 */, an + fmaxf(cur + an, 0.0f), 1e-36f);
+}
+
+// The whole tile (npairs candidate pairs in scan format) against one row point, in the reference's rounding,
+// by all 32 lanes of a warp: minimum and, if wanted, its lowest candidate index (tile-relative).
+template <bool WANT_INDEX>
+__device__ __forceinline__ void warp_tile_exact_min(const float4* tp, int npairs, float ax, float ay, float az, int lane,
+                                                    float& best, int& best_idx) {
+  const f32x2 ax2 = pack2(ax, ax), ay2 = pack2(ay, ay), az2 = pack2(az, az);
+  float e = __int_as_float(0x7f800000);
+  int ei = 0x7fffffff;
+  for (int q = lane; q < npairs; q += 32) {
+    const float4 q0 = tp[2 * q], q1 = tp[2 * q + 1];
+    const f32x2 dx = sub2(pack2(q0.x, q0.y), ax2);
+    const f32x2 dy = sub2(pack2(q0.z, q0.w), ay2);
+    const f32x2 dz = sub2(pack2(q1.x, q1.y), az2);
+    float lo, hi;
+    unpack2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lo, hi);
+    if (WANT_INDEX) {                       // q ascends: strict < keeps the lane's lowest index
+      if (lo < e) { e = lo; ei = 2 * q; }
+      if (hi < e) { e = hi; ei = 2 * q + 1; }
+    } else {
+      e = min3(e, lo, hi);
+    }
+  }
+  float m = e;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  best = m;
+  if (WANT_INDEX) best_idx = (int)__reduce_min_sync(0xffffffffu, e == m ? (unsigned)ei : 0x7fffffffu);
 }
 
 // NT threads per CTA. The register tile of R = 8 rows per thread is what makes the search FMA-bound
@@ -266,10 +318,10 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
       vmask = (unsigned long long)part[0] | ((unsigned long long)part[1] << 32);
     }
     // ---- search: which chunk of this tile holds the smallest |b|^2 - 2 a.b ----
-    float cur[R];
+    float cur[R], sec[R];
     int cid[R];
     #pragma unroll
-    for (int r = 0; r < R; ++r) { cur[r] = __int_as_float(0x7f800000); cid[r] = 0; }
+    for (int r = 0; r < R; ++r) { cur[r] = sec[r] = __int_as_float(0x7f800000); cid[r] = 0; }
     for (int c = 0; c < nch; ++c) {
       if (MERGED && !((vmask >> c) & 1ull)) continue;      // warp-uniform
       const float4* cp = tp + c * CH;
@@ -292,6 +344,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
       #pragma unroll
       for (int r = 0; r < R; ++r) {
         const bool better = cm[r] < cur[r];     // strict: the earliest chunk keeps bit-equal minima
+        sec[r] = fminf(sec[r], better ? cur[r] : cm[r]);      // runner-up: the smallest minimum of any other chunk
         cur[r] = better ? cm[r] : cur[r];
         cid[r] = better ? c : cid[r];
       }
@@ -346,6 +399,34 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
       }
     }
 
+    // ---- guard: a runner-up chunk inside the search's error window => the whole tile, exactly, for that row ----
+    if (!MERGED || vmask != 0ull) {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float ax, ay, az, dummy;
+        unpack2(nax[r], ax, dummy); unpack2(nay[r], ay, dummy); unpack2(naz[r], az, dummy);
+        ax *= -0.5f; ay *= -0.5f; az *= -0.5f;
+        const bool near_tie = K_ROW(r) < rowcount && sec[r] <= cur[r] + search_window(ax, ay, az, cur[r]);
+        unsigned flagged = __ballot_sync(0xffffffffu, near_tie);
+        while (flagged) {                         // warp-uniform; ~0.1 % of the (row, tile) pairs on LiDAR-like clouds
+          const int src = __ffs(flagged) - 1;
+          flagged &= flagged - 1;
+          float m;
+          int mi = 0;
+          warp_tile_exact_min<!MATRIX>(tp, nch * PR, __shfl_sync(0xffffffffu, ax, src), __shfl_sync(0xffffffffu, ay, src),
+                                       __shfl_sync(0xffffffffu, az, src), lane, m, mi);
+          if (lane == src) {
+            if (MATRIX) {
+              eb[r] = fminf(eb[r], m);
+            } else {
+              mi += t * TILE;
+              if (m < eb[r] || (m == eb[r] && mi < ei[r])) { eb[r] = m; ei[r] = mi; }
+            }
+          }
+        }
+      }
+    }
+
     }
 
     // ---- end of a (direction, row block): emit ----
@@ -375,8 +456,25 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
     const double S1 = block_sum<NT>(dsum, red);
     if (tid == 0) {
       const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
-      p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
-      if (p.symmetric && p.mirror && ci != cj) p.M[(long long)cj * p.ldm + ci] = v;
+      if (p.M) {
+        p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
+        if (p.symmetric && p.mirror && ci != cj) p.M[(long long)cj * p.ldm + ci] = v;
+      }
+      // fused _compute_cov_mmd / _compute_nna(k=1) reductions (reference cov_mmd_1nna.py:54-106): v >= 0, so
+      // (bits << 32 | index) orders by value, then by index -- torch's lowest-index tie rule on this path
+      if (p.keys) {
+        const int gi = p.offX + ci, gj = p.offY + cj;
+        if (gi != gj) {                                              // the +inf diagonal of _compute_nna
+          const unsigned long long vb = (unsigned long long)__float_as_uint(v) << 32;
+          atomicMin(p.keys + gj, vb | (unsigned)gi);
+          atomicMin(p.keys + gi, vb | (unsigned)gj);
+          const int lo = min(gi, gj), hi = max(gi, gj);
+          if (lo < p.n_ref && hi >= p.n_ref) {                       // an entry of M_rg: lo is the reference cloud
+            atomicMin(p.keys + p.n_total + hi, vb | (unsigned)lo);
+            atomicMin(p.keys + 2 * (long long)p.n_total + lo, vb | (unsigned)hi);
+          }
+        }
+      }
     }
   }
 }
@@ -772,9 +870,16 @@ extern "C" size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, i
   return s;
 }
 
-extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float* B, int nb, int pb, int row_begin,
-                                    int row_end, int row_stride, int flags, float* M, long long ldm, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+namespace {
+struct FusedKeys {            // fused MMD/COV/1-NNA epilogue of the matrix launch (null keys: off)
+  unsigned long long* keys = nullptr;
+  int n_total = 0, n_ref = 0, off_a = 0, off_b = 0;
+};
+}  // namespace
+
+static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, int pb, int row_begin, int row_end,
+                       int row_stride, int flags, float* M, long long ldm, const FusedKeys& fk, void* workspace,
+                       size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int symmetric = (flags & DUSTY_MATRIX_SYMMETRIC) != 0, mirror = (flags & DUSTY_MATRIX_MIRROR) != 0;
   const int compact_rows = (flags & DUSTY_MATRIX_COMPACT_ROWS) != 0, prepared = (flags & DUSTY_MATRIX_PREPARED) != 0;
@@ -782,11 +887,14 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   if (mirror && (!symmetric || compact_rows)) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: MIRROR needs SYMMETRIC and excludes COMPACT_ROWS");
   if (na < 0 || nb < 0 || pa <= 0 || pb <= 0) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: bad sizes na=%d pa=%d nb=%d pb=%d", na, pa, nb, pb);
   if (symmetric && (nb != na || pb != pa)) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: symmetric needs nb==na and pb==pa");
-  if (row_stride <= 0 || row_begin < 0 || row_end > na || ldm < nb)
+  if (row_stride <= 0 || row_begin < 0 || row_end > na || (M && ldm < nb))
     return fail_arg(DUSTY_EINVAL, "chamfer_matrix: bad row range [%d,%d) stride %d of %d, ldm %lld", row_begin, row_end, row_stride, na, ldm);
+  if (fk.keys && (fk.n_ref < 0 || fk.off_a < 0 || fk.off_b < 0 || fk.off_a + na > fk.n_total || fk.off_b + nb > fk.n_total ||
+                  (symmetric && fk.off_a != fk.off_b)))
+    return fail_arg(DUSTY_EINVAL, "chamfer_matrix_fused: offsets %d+%d, %d+%d do not fit %d stacked clouds", fk.off_a, na, fk.off_b, nb, fk.n_total);
   if (row_begin >= row_end || nb == 0) return 0;
   if (int rc = check_device()) return rc;
-  if (!A || !B || !M || !workspace) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: null pointer");
+  if (!A || !B || (!M && !fk.keys) || !workspace) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: null pointer");
   if (!aligned16(workspace)) return fail_arg(DUSTY_EALIGN, "chamfer_matrix: workspace must be 16-byte aligned");
   const size_t need = dusty_chamfer_matrix_workspace_bytes(na, pa, symmetric ? 0 : nb, pb);
   if (workspace_bytes < need) return fail_arg(DUSTY_ENOSPACE, "chamfer_matrix: workspace %zu < %zu", workspace_bytes, need);
@@ -833,6 +941,7 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
   p.row_begin = row_begin; p.row_stride = row_stride;
   p.symmetric = symmetric; p.mirror = mirror; p.compact_rows = compact_rows;
   p.M = M; p.ldm = ldm;
+  p.keys = fk.keys; p.n_total = fk.n_total; p.n_ref = fk.n_ref; p.offX = fk.off_a; p.offY = fk.off_b;
   const dim3 grid(nb, rows, 1);
   if (merge) {
     p.idx1 = reinterpret_cast<int*>(ma); p.idx2 = reinterpret_cast<int*>(mb);
@@ -840,4 +949,32 @@ extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float*
     return dispatch_nn<true, true>(merged_r, p, grid, st);
   }
   return dispatch_matrix(pa > pb ? pa : pb, p, grid, st);
+}
+
+extern "C" int dusty_chamfer_matrix(const float* A, int na, int pa, const float* B, int nb, int pb, int row_begin,
+                                    int row_end, int row_stride, int flags, float* M, long long ldm, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!M) return fail_arg(DUSTY_EINVAL, "chamfer_matrix: null pointer");
+  return matrix_impl(A, na, pa, B, nb, pb, row_begin, row_end, row_stride, flags, M, ldm, FusedKeys{}, workspace,
+                     workspace_bytes, stream);
+}
+
+extern "C" size_t dusty_nn_keys_bytes(int n_total) { return n_total > 0 ? (size_t)3 * n_total * sizeof(unsigned long long) : 0; }
+
+extern "C" int dusty_nn_keys_reset(uint64_t* keys, int n_total, void* stream) {
+  if (n_total <= 0) return 0;
+  if (!keys) return fail_arg(DUSTY_EINVAL, "nn_keys_reset: null pointer");
+  DUSTY_CUDA(cudaMemsetAsync(keys, 0xff, dusty_nn_keys_bytes(n_total), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int dusty_chamfer_matrix_fused(const float* A, int na, int pa, const float* B, int nb, int pb, int row_begin,
+                                          int row_end, int row_stride, int flags, float* M, long long ldm, int stacked_offset_a,
+                                          int stacked_offset_b, int n_ref, int n_total, uint64_t* keys, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (!keys) return fail_arg(DUSTY_EINVAL, "chamfer_matrix_fused: null keys");
+  FusedKeys fk;
+  fk.keys = reinterpret_cast<unsigned long long*>(keys);
+  fk.n_total = n_total; fk.n_ref = n_ref; fk.off_a = stacked_offset_a; fk.off_b = stacked_offset_b;
+  return matrix_impl(A, na, pa, B, nb, pb, row_begin, row_end, row_stride, flags, M, ldm, fk, workspace, workspace_bytes, stream);
 }

@@ -109,6 +109,43 @@ __global__ void __launch_bounds__(TPB) final_kernel(int nr, int ng, const int* _
   }
 }
 
+// Fused path: the matrix kernel's epilogue left packed (value bits << 32 | stacked index) minima, one set of
+// 3 (nr+ng) keys per row shard (after the all-gather: `shards` sets). Reduce over the shards and fill the same
+// scratch vectors the column / row kernels produce, so that final_kernel -- and hence every score -- is shared.
+__global__ void __launch_bounds__(TPB) keys_kernel(const unsigned long long* __restrict__ keys, int shards, int nr, int ng,
+                                                   int* __restrict__ nn_label, float* __restrict__ colmin,
+                                                   float* __restrict__ rowmin, int* __restrict__ covered) {
+  const int n = nr + ng;
+  const int c = blockIdx.x * TPB + threadIdx.x;
+  if (c >= n) return;
+  unsigned long long all = ~0ull, other = ~0ull;
+  const int which = c < nr ? 2 : 1;            // reference clouds: nearest generated one; generated: nearest reference
+  for (int s = 0; s < shards; ++s) {
+    const unsigned long long* k = keys + (size_t)s * 3 * n;
+    all = min(all, k[c]);
+    other = min(other, k[(size_t)which * n + c]);
+  }
+  nn_label[c] = ((int)(unsigned)all < nr) ? 1 : 0;
+  const float v = __uint_as_float((unsigned)(other >> 32));
+  if (c < nr) {
+    rowmin[c] = v;
+  } else {
+    colmin[c - nr] = v;
+    const int ref = (int)(unsigned)other;
+    if (ref >= 0 && ref < nr) covered[ref] = 1;
+  }
+}
+
+// (G, cap, n) gathered compact row blocks of the cyclic deal (block g, row r = global row g + r G, entries j >= i
+// valid) -> full symmetric (n, n) matrix, every entry read from the shard that computed it.
+__global__ void __launch_bounds__(TPB) symmetric_kernel(const float* __restrict__ blocks, int G, int cap, int n,
+                                                        float* __restrict__ out, long long ldo) {
+  const int j = blockIdx.x * TPB + threadIdx.x, i = blockIdx.y;
+  if (j >= n) return;
+  const int r = i <= j ? i : j, c = i <= j ? j : i;
+  out[(long long)i * ldo + j] = blocks[((size_t)(r % G) * cap + r / G) * n + c];
+}
+
 }  // namespace metrics
 }  // namespace dusty
 
@@ -138,5 +175,38 @@ extern "C" int dusty_cov_mmd_1nna_finalize(const float* Mrr, const float* Mrg, c
   DUSTY_AFTER_LAUNCH("metrics row_kernel");
   final_kernel<<<1, TPB, 0, st>>>(nr, ng, nn_label, colmin, rowmin, covered, out7);
   DUSTY_AFTER_LAUNCH("metrics final_kernel");
+  return 0;
+}
+
+extern "C" int dusty_cov_mmd_1nna_from_keys(const uint64_t* keys, int shards, int nr, int ng, float* out7, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nr <= 0 || ng <= 0 || shards <= 0) return fail_arg(DUSTY_EINVAL, "cov_mmd_1nna_from_keys: nr=%d ng=%d shards=%d must be positive", nr, ng, shards);
+  if (int rc = check_device()) return rc;
+  if (!keys || !out7 || !workspace) return fail_arg(DUSTY_EINVAL, "cov_mmd_1nna_from_keys: null pointer");
+  if (workspace_bytes < dusty_cov_mmd_1nna_workspace_bytes(nr, ng)) return fail_arg(DUSTY_ENOSPACE, "cov_mmd_1nna_from_keys: workspace too small");
+  int* nn_label = static_cast<int*>(workspace);
+  float* colmin = reinterpret_cast<float*>(nn_label + nr + ng);
+  float* rowmin = colmin + ng;
+  int* covered = reinterpret_cast<int*>(rowmin + nr);
+  DUSTY_CUDA(cudaMemsetAsync(covered, 0, sizeof(int) * nr, st));
+  keys_kernel<<<(nr + ng + TPB - 1) / TPB, TPB, 0, st>>>(reinterpret_cast<const unsigned long long*>(keys), shards, nr, ng,
+                                                          nn_label, colmin, rowmin, covered);
+  DUSTY_AFTER_LAUNCH("metrics keys_kernel");
+  final_kernel<<<1, TPB, 0, st>>>(nr, ng, nn_label, colmin, rowmin, covered, out7);
+  DUSTY_AFTER_LAUNCH("metrics final_kernel");
+  return 0;
+}
+
+extern "C" int dusty_symmetric_from_shards(const float* blocks, int shards, int cap, int n, float* out, long long ldo,
+                                           void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n < 0 || shards <= 0 || cap < 0 || (long long)shards * cap < n || ldo < n || n > 65535)
+    return fail_arg(DUSTY_EINVAL, "symmetric_from_shards: shards=%d cap=%d n=%d ldo=%lld", shards, cap, n, ldo);
+  if (n == 0) return 0;
+  if (int rc = check_device()) return rc;
+  if (!blocks || !out) return fail_arg(DUSTY_EINVAL, "symmetric_from_shards: null pointer");
+  symmetric_kernel<<<dim3((n + TPB - 1) / TPB, n), TPB, 0, st>>>(blocks, shards, cap, n, out, ldo);
+  DUSTY_AFTER_LAUNCH("metrics symmetric_kernel");
   return 0;
 }

@@ -1,9 +1,11 @@
 """Point-drop heads of DUSty-GAN on libdustyb200 (mirror of reference models/dusty.py).
 
 Same class names, constructor arguments, attribute names (``fixed_noise``, ``drop_const``,
-``gumbel``, ``gumbel_pixel``, ``gumbel_image``) and output-dict keys as the reference, so
-``utils.setup``'s fixed-noise pre-hook (reference utils/__init__.py:141-149) keeps working on these
-modules unchanged. The element-wise chains run as single CUDA kernels through the C ABI.
+``gumbel``, ``gumbel_pixel``, ``gumbel_image``) and output-dict keys as the reference.
+``utils.setup``'s fixed-noise forward pre-hook (reference utils/__init__.py:141-149) is registered on the
+GumbelSigmoid modules; the fused heads do not call those modules, so ``_head_call`` runs their pre-hooks
+itself before reading ``fixed_noise`` (``tests/test_gpu_head.py::test_setup_fixed_noise_hook_*``). The
+element-wise chains run as single CUDA kernels through the C ABI.
 """
 import ctypes as C
 
@@ -12,6 +14,21 @@ import torch
 from torch import nn
 
 from .. import _lib
+
+
+def _run_forward_pre_hooks(module, logits):
+    """The fused heads read a gate's state without going through ``Module.__call__``, so the gate's forward
+    pre-hooks are run here, with the arguments ``__call__`` would pass. ``utils.setup(fix_noise=True)`` relies on
+    one: its ``set_gumbel_noise`` hook freezes ``fixed_noise`` on the first call (reference
+    utils/__init__.py:141-149). A hook that returns replacement inputs is not supported on the fused path."""
+    for hook_id, hook in list(module._forward_pre_hooks.items()):
+        if hook_id in getattr(module, "_forward_pre_hooks_with_kwargs", {}):
+            result = hook(module, (logits,), {})
+        else:
+            result = hook(module, (logits,))
+        if result is not None:
+            raise NotImplementedError("a forward pre-hook that replaces the gate's input is not supported by the fused "
+                                      "head; call GumbelSigmoid directly")
 
 
 def _gate_struct(module, logits):
@@ -180,12 +197,15 @@ def _head_call(module, output, threshold, lidar=None, tol=1e-8, points_layout=1,
     p.b, p.h, p.w, p.conf_channels = B, H, W, channels
     keep = []
     if channels == 1:
+        _run_forward_pre_hooks(module.gumbel, c)
         p.gate_pixel, k = _gate_struct(module.gumbel, c)
         keep.append(k)
     else:
+        _run_forward_pre_hooks(module.gumbel_pixel, c[:, :1])
         p.gate_pixel, k = _gate_struct(module.gumbel_pixel, c[:, :1])
         keep.append(k)
-        if module.training:
+        if module.training:     # the reference calls the image gate in training mode only (models/dusty.py:117-120)
+            _run_forward_pre_hooks(module.gumbel_image, c[:, 1:])
             p.gate_image, k = _gate_struct(module.gumbel_image, c[:, 1:])
             keep.append(k)
         else:

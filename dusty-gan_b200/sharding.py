@@ -2,17 +2,26 @@
 
 The reference is single-GPU on this path; the matrix entries are independent, so
 rank r computes rows r, r+G, r+2G, ... of the symmetric stacked matrix (a cyclic deal balances the
-triangular work: row i has n-i entries) into a compact (rows_owned, n) block, and ONE all-gather of
-those blocks gives every rank the whole upper triangle. No other collective is on the path. Entry
-values do not depend on G: each entry is produced by one CTA with a fixed reduction order.
+triangular work: row i has n-i entries). Two ways to combine the shards, one collective each:
+
+* scores (``compute_cov_mmd_1nna``): the matrix kernel's epilogue reduces every entry into per-cloud packed
+  (value, index) minima (``dusty_chamfer_matrix_fused``); the ranks all-gather those vectors -- 24 bytes per
+  stacked cloud and rank, 48 KB at 1000 vs 1000 -- and no rank ever holds an n x n tensor;
+* the matrix itself (``pairwise_matrices`` / ``_pairwise_distance``): compact (rows_owned, n) blocks, one
+  all-gather, assembled into the full symmetric matrix by one kernel (``dusty_symmetric_from_shards``).
+
+Entry values do not depend on G: each entry is produced by one CTA with a fixed reduction order.
 """
 import torch
 import torch.distributed as dist
 
+from . import _lib
 
-def world():
+
+def world(group=None):
+    """(rank, world size) of ``group`` (default process group when None); (0, 1) without torch.distributed."""
     if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
+        return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
 
 
@@ -26,38 +35,58 @@ def rows_per_rank(n, world_size):
     return (n + world_size - 1) // world_size
 
 
-def assemble_upper(blocks, n, world_size):
-    """(G, cap, n) gathered compact blocks -> (n, n) matrix whose upper triangle (incl. diagonal) is valid."""
-    cap = blocks.shape[1]
-    # block g row r is global row g + r*G: interleave
-    full = blocks.permute(1, 0, 2).reshape(cap * world_size, blocks.shape[2])
-    return full[:n]
+def shard_of_row(i, world_size):
+    """(rank, row inside that rank's compact block) holding global row ``i`` under the cyclic deal."""
+    return i % world_size, i // world_size
 
 
-def symmetrize_upper(U):
-    """Mirror the strict upper triangle into the lower one (entries are bit-equal in the reference,
-    SURVEY.md S8)."""
-    upper = torch.triu(U)
-    return upper + torch.triu(U, diagonal=1).t()
+def pack_key(value_f32_bits, index):
+    """The epilogue's packed minimum: float bits of a (non-negative) matrix entry << 32 | stacked index, so
+    that an unsigned 64-bit min orders by value, then by index (csrc/chamfer.cu, nn_kernel epilogue)."""
+    return (int(value_f32_bits) << 32) | int(index)
+
+
+def assemble_symmetric(blocks, n):
+    """(G, cap, n) gathered compact blocks -> full symmetric (n, n) matrix (one kernel; entries below the
+    diagonal are read from their mirror, bit-equal in the reference)."""
+    G, cap, width = blocks.shape
+    assert width == n and blocks.is_contiguous()
+    out = torch.empty(n, n, device=blocks.device, dtype=torch.float32)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(blocks.device):
+        _lib.check(lib.dusty_symmetric_from_shards(_lib.ptr(blocks), G, cap, n, _lib.ptr(out), out.stride(0),
+                                                   _lib.stream_of(blocks)), "dusty_symmetric_from_shards")
+    return out
 
 
 def all_gather_blocks(mine, group=None):
-    """The single collective on the path: (cap, n) per rank -> (G, cap, n) on every rank."""
-    _, G = world()
+    """The single collective of the matrix path: (cap, n) per rank -> (G, cap, n) on every rank."""
+    _, G = world(group)
     flat = torch.empty(G * mine.shape[0], mine.shape[1], device=mine.device, dtype=mine.dtype)
     dist.all_gather_into_tensor(flat, mine.contiguous(), group=group)
     return flat.view(G, mine.shape[0], mine.shape[1])
 
 
+def all_gather_keys(keys, group=None):
+    """The single collective of the score path: (3 n,) int64 packed minima per rank -> (G, 3 n)."""
+    _, G = world(group)
+    if G == 1:
+        return keys.view(1, -1)
+    out = torch.empty(G * keys.numel(), device=keys.device, dtype=keys.dtype)
+    dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    return out.view(G, keys.numel())
+
+
 def symmetric_chamfer_matrix(clouds, group=None):
     """Full symmetric (n,n) Chamfer matrix of ``clouds`` (n,P,3); every rank returns the same tensor."""
     from .utils.metrics.cov_mmd_1nna import chamfer_matrix
-    rank, G = world()
+    rank, G = world(group)
     n = clouds.size(0)
     if G == 1:
         return chamfer_matrix(clouds)
     cap = rows_per_rank(n, G)
     mine = torch.zeros(cap, n, device=clouds.device, dtype=torch.float32)
     chamfer_matrix(clouds, None, rows=owned_rows(n, rank, G), compact_rows=True, out=mine)
-    gathered = all_gather_blocks(mine, group)
-    return symmetrize_upper(assemble_upper(gathered, n, G))
+    return assemble_symmetric(all_gather_blocks(mine, group), n)

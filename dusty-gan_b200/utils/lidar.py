@@ -14,6 +14,37 @@ from torch import nn
 from .. import _lib
 
 
+class _InvToXYZ(torch.autograd.Function):
+    """``Coordinate.inv_to_xyz`` with the gradient the reference's op chain has (utils/lidar.py:38-47,61-68):
+    forward is the CUDA kernel; backward differentiates d = valid * ((1/disp - min) / range * range + min) / max,
+    disp = inv * (1/min - 1/max) + 1/max, times the (constant) direction of every pixel. The backward pass is
+    off the evaluate path (demo.py's inversion loss uses it) and is plain torch arithmetic."""
+
+    @staticmethod
+    def forward(ctx, inv, coord, tol):
+        B = inv.shape[0]
+        out = torch.empty(B, 3, coord.H, coord.W, device=inv.device, dtype=torch.float32)
+        p = coord._params(B, tol, 0)
+        lib = _lib.load()
+        with torch.cuda.device(inv.device):
+            _lib.check(lib.dusty_inv_to_xyz(C.byref(p), _lib.ptr(inv), _lib.ptr(coord.trig_table(inv.device)),
+                                            _lib.ptr(out), _lib.stream_of(inv)), "dusty_inv_to_xyz")
+        ctx.coord, ctx.tol = coord, tol
+        ctx.save_for_backward(inv)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_xyz):
+        (inv,) = ctx.saved_tensors
+        c = ctx.coord
+        t = c.trig_table(inv.device)
+        valid = ((inv - c.drop_const).abs() > ctx.tol).float()
+        disp = inv * (1 / c.min_depth - 1 / c.max_depth) + 1 / c.max_depth
+        ddepth = -(1 / c.min_depth - 1 / c.max_depth) / (disp * disp) / c.max_depth * valid      # d(range)/d(inv)
+        direction = torch.stack([t[0] * t[2], t[0] * t[3], t[1]])[None]                          # (1,3,H,W)
+        return (grad_xyz * direction).sum(dim=1, keepdim=True) * ddepth, None, None
+
+
 class Coordinate(nn.Module):
     def __init__(self, min_depth, max_depth, shape, drop_const=0) -> None:
         super().__init__()
@@ -74,19 +105,13 @@ class Coordinate(nn.Module):
         return p
 
     def inv_to_xyz(self, inv_depth, tol=1e-8):
-        """Normalised inverse depth (B,1,H,W) in [0,1] -> xyz (B,3,H,W); dropped pixels map to the origin."""
+        """Normalised inverse depth (B,1,H,W) in [0,1] -> xyz (B,3,H,W); dropped pixels map to the origin.
+        Differentiable with respect to ``inv_depth`` like the reference's op chain."""
         _lib.require_cuda(inv_depth, "inv_depth")
         if inv_depth.dim() != 4 or inv_depth.shape[1:] != (1, self.H, self.W):
             raise ValueError(f"expected (B,1,{self.H},{self.W}), got {tuple(inv_depth.shape)}")
-        inv = inv_depth.contiguous()
-        B = inv.shape[0]
-        out = torch.empty(B, 3, self.H, self.W, device=inv.device, dtype=torch.float32)
-        p = self._params(B, tol, 0)
-        lib = _lib.load()
-        with torch.cuda.device(inv.device):
-            _lib.check(lib.dusty_inv_to_xyz(C.byref(p), _lib.ptr(inv), _lib.ptr(self.trig_table(inv.device)),
-                                            _lib.ptr(out), _lib.stream_of(inv)), "dusty_inv_to_xyz")
-        return out
+        self._params(1, tol, 0)       # argument checks before the autograd node is built
+        return _InvToXYZ.apply(inv_depth.contiguous(), self, tol)
 
     def pol_to_xyz(self, polar):
         """Range image (B,1,H,W) -> xyz (B,3,H,W) (reference utils/lidar.py:49-56); set-up helper."""

@@ -4,9 +4,16 @@ utils/metrics/cov_mmd_1nna.py:19-139).
 The reference fills each matrix with a Python double loop (one row, 512 columns per iteration,
 >= 9 kernel launches each). Here one launch computes a whole matrix -- or, when the two sets have
 the same number of points per cloud, ONE launch computes the upper triangle of the stacked
-(N_ref+N_gen)^2 matrix that holds M_rr, M_rg and M_gg at once. When ``torch.distributed`` is
-initialised with more than one rank the rows of that matrix are sharded over the ranks and
-combined by a single all-gather (see ``sharding.py``).
+(N_ref+N_gen)^2 matrix that holds M_rr, M_rg and M_gg at once. ``compute_cov_mmd_1nna`` goes one step
+further: the min / arg-min / top-1 reductions of ``_compute_cov_mmd`` and ``_compute_nna`` are fused into
+that launch's epilogue, so no N x N tensor exists at all (``fused_scores``). When ``torch.distributed`` is
+initialised with more than one rank the rows are sharded over the ranks and combined by a single
+all-gather -- of the per-cloud (min, arg-min) vectors for the scores, of row blocks for the matrices
+(see ``sharding.py``).
+
+Distances are exactly the reference CUDA kernel's for finite inputs (csrc/chamfer.cu: the |b|^2 - 2 a.b
+search is only trusted outside its own rounding window; inside it the tile is re-evaluated in the
+reference's rounding), so arg-mins and the scores built on them do not flip on near-ties.
 """
 import numpy as np
 import torch
@@ -31,6 +38,10 @@ def _check_clouds(pcs, name):
     return pcs.contiguous()
 
 
+# compute_cov_mmd_1nna: reductions fused into the matrix kernel's epilogue (no N x N tensor). False selects
+# the round-1 path (matrices + finaliser kernels); both give bit-identical scores (tests/test_gpu_metrics.py).
+FUSED_EPILOGUE = True
+
 # Clouds with more points than this are taken to be un-sampled range images, whose dropped pixels are
 # all the same (0,0,0) point (reference evaluate_reconstruction.py:124-131): the kernel
 # then scans one origin point of that multiplicity per cloud. The choice depends on the shape only, so
@@ -38,11 +49,14 @@ def _check_clouds(pcs, name):
 MERGE_ORIGIN_ABOVE = 4096
 
 
-def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None, merge_origin=None):
+def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None, merge_origin=None, fused=None):
     """M[i,j] = compute_cd(pcs_1[i], pcs_2[j]) in one launch. ``pcs_2=None`` declares the symmetric
     case (upper triangle computed, mirrored unless ``compact_rows``). ``rows=(begin,end,stride)``
     restricts the computation to a row shard. ``merge_origin`` (default: by point count, see
-    ``MERGE_ORIGIN_ABOVE``) collapses each cloud's exactly-zero points into one weighted point."""
+    ``MERGE_ORIGIN_ABOVE``) collapses each cloud's exactly-zero points into one weighted point.
+    ``fused=(keys, stacked_offset_1, stacked_offset_2, n_ref, n_total)`` also reduces every entry into the
+    packed minima ``keys`` (int64, 3 n_total; see ``fused_scores``); with ``out=False`` the matrix is then
+    not stored at all."""
     a = _check_clouds(pcs_1, "pcs_1")
     symmetric = pcs_2 is None
     b = a if symmetric else _check_clouds(pcs_2, "pcs_2")
@@ -61,10 +75,13 @@ def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None, m
         merge_origin = max(pa, pb) > MERGE_ORIGIN_ABOVE
     if merge_origin:
         flags |= _lib.MATRIX_MERGE_ORIGIN
+    store = out is not False
+    if not store and fused is None:
+        raise ValueError("out=False needs fused=...")
     if out is None:
         out = torch.zeros(nrows if compact_rows else na, nb, device=a.device, dtype=torch.float32)
     if na == 0 or nb == 0 or nrows == 0:
-        return out
+        return out if store else None
     if pa == 0 or pb == 0:
         raise ValueError("clouds must hold at least one point")
     lib = _lib.load()
@@ -74,13 +91,22 @@ def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None, m
         if KERNEL_EVENTS is not None:       # bench.py: device time of the launch on its own stream
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.check(lib.dusty_chamfer_matrix(_lib.ptr(a), na, pa, _lib.ptr(b), nb, pb, begin, end, stride, flags,
-                                            _lib.ptr(out), out.stride(0), _lib.ptr(ws), nbytes, _lib.stream_of(a)),
-                   "dusty_chamfer_matrix")
+        m_ptr, ldm = (_lib.ptr(out), out.stride(0)) if store else (None, 0)
+        if fused is None:
+            _lib.check(lib.dusty_chamfer_matrix(_lib.ptr(a), na, pa, _lib.ptr(b), nb, pb, begin, end, stride, flags,
+                                                m_ptr, ldm, _lib.ptr(ws), nbytes, _lib.stream_of(a)),
+                       "dusty_chamfer_matrix")
+        else:
+            keys, off_1, off_2, n_ref, n_total = fused
+            assert keys.dtype == torch.int64 and keys.numel() == 3 * n_total and keys.is_contiguous()
+            _lib.check(lib.dusty_chamfer_matrix_fused(_lib.ptr(a), na, pa, _lib.ptr(b), nb, pb, begin, end, stride, flags,
+                                                      m_ptr, ldm, off_1, off_2, n_ref, n_total, _lib.ptr(keys),
+                                                      _lib.ptr(ws), nbytes, _lib.stream_of(a)),
+                       "dusty_chamfer_matrix_fused")
         if KERNEL_EVENTS is not None:
             ev[1].record()
             KERNEL_EVENTS.append(ev)
-    return out
+    return out if store else None
 
 
 def _pairwise_distance(pcs_1, pcs_2, batch_size, metrics=("cd",), verbose=True):
@@ -170,6 +196,42 @@ def pairwise_matrices(pcs_gen, pcs_ref):
     return chamfer_matrix(ref), chamfer_matrix(ref, gen), chamfer_matrix(gen)
 
 
+def fused_scores(pcs_gen, pcs_ref, group=None):
+    """(cov/mmd dict, 1-NNA dict) without ever storing a matrix: every entry the matrix kernel computes is
+    reduced on the spot into three packed (value, index) minima per stacked cloud (reference first, then
+    generated: the order of _compute_nna's matrix, reference cov_mmd_1nna.py:71-79). Ranks of ``group``
+    work on a cyclic row shard each and all-gather those vectors (24 B per cloud and rank)."""
+    gen = _check_clouds(pcs_gen, "pcs_gen")
+    ref = _check_clouds(pcs_ref, "pcs_ref")
+    nr, ng = ref.size(0), gen.size(0)
+    n = nr + ng
+    if nr == 0 or ng == 0:
+        raise ValueError("both sets must hold at least one cloud")
+    rank, G = sharding.world(group)
+    lib = _lib.load()
+    keys = torch.empty(3 * n, device=ref.device, dtype=torch.int64)
+    with torch.cuda.device(ref.device):
+        _lib.check(lib.dusty_nn_keys_reset(_lib.ptr(keys), n, _lib.stream_of(keys)), "dusty_nn_keys_reset")
+    if ref.size(1) == gen.size(1):      # one stacked symmetric launch fills M_rr, M_rg and M_gg's reductions
+        stacked = torch.cat([ref, gen], dim=0)
+        chamfer_matrix(stacked, None, rows=sharding.owned_rows(n, rank, G), compact_rows=True, out=False,
+                       fused=(keys, 0, 0, nr, n))
+    else:
+        chamfer_matrix(ref, None, rows=sharding.owned_rows(nr, rank, G), compact_rows=True, out=False, fused=(keys, 0, 0, nr, n))
+        chamfer_matrix(ref, gen, rows=sharding.owned_rows(nr, rank, G), compact_rows=True, out=False, fused=(keys, 0, nr, nr, n))
+        chamfer_matrix(gen, None, rows=sharding.owned_rows(ng, rank, G), compact_rows=True, out=False, fused=(keys, nr, nr, nr, n))
+    gathered = sharding.all_gather_keys(keys, group)
+    nbytes = lib.dusty_cov_mmd_1nna_workspace_bytes(nr, ng)
+    ws = _lib.workspace(nbytes, ref.device)
+    out = torch.empty(7, device=ref.device, dtype=torch.float32)
+    with torch.cuda.device(ref.device):
+        _lib.check(lib.dusty_cov_mmd_1nna_from_keys(_lib.ptr(gathered), gathered.size(0), nr, ng, _lib.ptr(out), _lib.ptr(ws),
+                                                    nbytes, _lib.stream_of(ref)), "dusty_cov_mmd_1nna_from_keys")
+    o = [float(v) for v in out.tolist()]
+    cov_mmd = {"mmd": o[0], "mmd-sample": o[1], "cov": float(o[2]) / float(nr)}
+    return cov_mmd, _nna_scores(o[3], o[4], o[5], o[6], n)
+
+
 @torch.no_grad()
 def compute_cov_mmd_1nna(pcs_gen, pcs_ref, batch_size, metrics=("cd",), verbose=True):
     assert isinstance(metrics, tuple)
@@ -178,8 +240,11 @@ def compute_cov_mmd_1nna(pcs_gen, pcs_ref, batch_size, metrics=("cd",), verbose=
     results = {}
     if "cd" not in metrics:
         return results
-    M_rr, M_rg, M_gg = pairwise_matrices(pcs_gen, pcs_ref)
-    cov_mmd, nna = _finalize_device(M_rr, M_rg, M_gg)
+    if FUSED_EPILOGUE:
+        cov_mmd, nna = fused_scores(pcs_gen, pcs_ref)
+    else:       # the three matrices, then three small kernels over them (kept for A/B tests)
+        M_rr, M_rg, M_gg = pairwise_matrices(pcs_gen, pcs_ref)
+        cov_mmd, nna = _finalize_device(M_rr, M_rg, M_gg)
     for k, v in cov_mmd.items():
         results.update({"{}-{}".format(k, "cd"): v})
     for k, v in nna.items():

@@ -81,8 +81,14 @@ gather_operation = GatherOperation.apply
 
 def downsample_point_clouds(xyz, k):
     """(B,N,3) -> (B,k,3): FPS indices and the gather in one kernel launch (the reference makes two
-    full copies of the cloud and launches two kernels, fps/furthest_point_sampling.py:84-93)."""
+    full copies of the cloud and launches two kernels, fps/furthest_point_sampling.py:84-93). When a
+    gradient is required the gather goes through ``gather_operation`` so that it flows back to ``xyz``."""
     assert xyz.ndim == 3, "expected 3-dim, but got {}-dim tensor".format(xyz.ndim)
     assert xyz.size(2) == 3, "expected (B,N,3), but got {}".format(xyz.shape)
     assert xyz.is_cuda
+    if torch.is_grad_enabled() and xyz.requires_grad:
+        # the reference's composition (fps/furthest_point_sampling.py:88-92): non-differentiable indices, then
+        # GatherOperation, whose backward scatters the gradient to the sampled points
+        inds = furthest_point_sampling(xyz, k)
+        return gather_operation(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2)
     return _fps(xyz, k, True)[1]

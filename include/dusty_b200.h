@@ -17,6 +17,12 @@
  *   dusty_chamfer_matrix         utils/metrics/cov_mmd_1nna.py:24-51 (_pairwise_distance, the Python
  *                                double loop over compute_cd, :19-21)
  *   dusty_cov_mmd_1nna_finalize  utils/metrics/cov_mmd_1nna.py:54-106 (_compute_cov_mmd, _compute_nna k=1)
+ *   dusty_chamfer_matrix_fused, dusty_nn_keys_*, dusty_cov_mmd_1nna_from_keys
+ *                                utils/metrics/cov_mmd_1nna.py:109-139 (compute_cov_mmd_1nna): the three
+ *                                _pairwise_distance calls with the min / arg-min / topk reductions of :54-106
+ *                                folded into the matrix kernel's epilogue -- no (Nr+Ng)^2 tensor is ever stored
+ *   dusty_symmetric_from_shards  the multi-GPU assembly of a row-sharded symmetric matrix (no reference
+ *                                counterpart: the reference is single-GPU on this path)
  *   dusty_jsd_vote, dusty_jsd_from_counts   utils/metrics/jsd.py:23-92, 110-121 (entropy_of_occupancy_grid,
  *                                _jensen_shannon_divergence)
  *   dusty_fps                    utils/sampling/fps/furthest_point_sampling.cpp:79-100
@@ -45,7 +51,7 @@
 extern "C" {
 #endif
 
-#define DUSTY_B200_ABI_VERSION 1
+#define DUSTY_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DUSTY_API __attribute__((visibility("default")))
@@ -131,6 +137,39 @@ DUSTY_API int dusty_chamfer_matrix(const float* A, int na, int pa, const float* 
                          int row_begin, int row_end, int row_stride, int flags,
                          float* M, long long ldm,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused evaluation (compute_cov_mmd_1nna, reference cov_mmd_1nna.py:109-139): the same launch as
+ * dusty_chamfer_matrix, and every computed entry (i, j) also feeds the reductions _compute_cov_mmd and
+ * _compute_nna(k = 1) need, as 64-bit atomic minima of (float bits of M[i,j] << 32 | stacked index):
+ *   keys[0*n_total + c]  nearest other cloud of stacked cloud c (the +inf diagonal of :82 is skipped);
+ *   keys[1*n_total + c]  for a generated cloud c: its nearest reference cloud   (MMD-sample, COV);
+ *   keys[2*n_total + c]  for a reference cloud c: its nearest generated cloud   (MMD).
+ * "Stacked" is the order of _compute_nna's matrix: the n_ref reference clouds first, then the generated
+ * ones; cloud i of A is stacked cloud stacked_offset_a + i, cloud j of B is stacked_offset_b + j. Every
+ * unordered pair of stacked clouds must be computed by exactly one launch / row shard (one symmetric launch
+ * over the stacked set, or M_rr, M_rg, M_gg as three launches). Ties resolve to the lowest stacked index.
+ * M may be NULL: then the matrix is not stored at all -- peak memory is O(n_total), not O(n_total^2).
+ * keys (3*n_total u64) must be reset with dusty_nn_keys_reset before the first launch of an evaluation.
+ * Across GPUs every rank fills its own key set from its row shard; the sets are all-gathered (24*n_total
+ * bytes per rank) and dusty_cov_mmd_1nna_from_keys reduces over them. */
+DUSTY_API size_t dusty_nn_keys_bytes(int n_total);
+DUSTY_API int dusty_nn_keys_reset(uint64_t* keys, int n_total, void* stream);
+DUSTY_API int dusty_chamfer_matrix_fused(const float* A, int na, int pa, const float* B, int nb, int pb,
+                         int row_begin, int row_end, int row_stride, int flags,
+                         float* M, long long ldm,
+                         int stacked_offset_a, int stacked_offset_b, int n_ref, int n_total, uint64_t* keys,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* out7 as dusty_cov_mmd_1nna_finalize, from `shards` gathered key sets (shards * 3 * (nr+ng) u64, set s at
+ * keys + s*3*(nr+ng)); workspace: dusty_cov_mmd_1nna_workspace_bytes(nr, ng). */
+DUSTY_API int dusty_cov_mmd_1nna_from_keys(const uint64_t* keys, int shards, int nr, int ng, float* out7,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Full symmetric (n,n) matrix from the gathered compact row blocks of a cyclic row deal: blocks (shards, cap, n),
+ * block g row r = global row g + r*shards, entries j >= i valid (DUSTY_MATRIX_SYMMETRIC | COMPACT_ROWS). Every
+ * entry of out is read from the shard that computed it (M[i,j] for i > j comes from M[j,i]: bit-equal in the
+ * reference). n <= 65535. */
+DUSTY_API int dusty_symmetric_from_shards(const float* blocks, int shards, int cap, int n, float* out, long long ldo,
+                                void* stream);
 
 /* MMD / COV / 1-NNA from the three matrices, on the device (no host round trip).
  *   Mrr (nr,nr), Mrg (nr,ng), Mgg (ng,ng) row-major f32, contiguous.

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert exported == declared_symbols()
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.dusty_abi_version() == 1
+    assert lib.dusty_abi_version() == _lib.ABI_VERSION == 2
     assert lib.dusty_launch_count() == 0 or lib.dusty_launch_count() > 0
 
 

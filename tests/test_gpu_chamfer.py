@@ -9,7 +9,14 @@ from oracle import native, refload
 
 pytestmark = pytest.mark.gpu
 
-REL_TOL = 1e-5      # north_star: Chamfer within 1e-5 relative (FP32)
+REL_TOL = 1e-5      # north_star: Chamfer within 1e-5 relative (FP32) -- the bar against the reference's CPU twin
+ULP = 2.0 ** -23    # matrix entries against the CUDA-rounding oracle: per-point distances are bit-equal, the two
+                    # double-accumulated means can differ in the last place of their f32 rounding
+
+
+def assert_entries_equal(M, O):
+    """Every entry within one ulp of the oracle's (exactly equal almost everywhere)."""
+    assert np.all(np.abs(M.astype(np.float64) - O) <= ULP * np.abs(O)), np.abs(M - O).max()
 
 
 def cuda(a):
@@ -33,18 +40,14 @@ def run_forward(xyz1, xyz2):
     return d1.cpu().numpy(), d2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy()
 
 
-def check_against_oracle(xyz1, xyz2, exact_fraction=0.999):
+def check_against_oracle(xyz1, xyz2):
+    """Distances AND arg-mins bit-equal to the reference CUDA kernel's restatement: the |b|^2 - 2 a.b search
+    only proposes, every returned value is the reference formula's minimum (csrc/chamfer.cu, guard)."""
     d1, d2, i1, i2 = run_forward(xyz1, xyz2)
     o1, o2, j1, j2 = native.chamfer_forward(xyz1, xyz2, rounding="cuda")
-    for d, o, i, j, other in ((d1, o1, i1, j1, xyz2), (d2, o2, i2, j2, xyz1)):
-        assert np.all(d >= o), "a reported distance can never be below the true minimum"
-        assert rel_err(d, o)[o > 0].max(initial=0.0) <= REL_TOL
-        assert np.all(d[o == 0] <= 1e-12)
-        same = d == o
-        assert same.mean() >= exact_fraction
-        assert np.all(i >= 0) and np.all(i < other.shape[1])
-        # wherever the value is the reference's minimum the index is the reference's (lowest on ties)
-        assert np.array_equal(i[same], j[same])
+    for d, o, i, j in ((d1, o1, i1, j1), (d2, o2, i2, j2)):
+        assert np.array_equal(d, o), (np.abs(d - o).max(), (d != o).mean())
+        assert np.array_equal(i, j), (i != j).mean()
     return d1, d2, i1, i2
 
 
@@ -95,9 +98,7 @@ def test_forward_against_reference_cuda_kernel():
     torch.cuda.synchronize()
     d1, d2, i1, i2 = run_forward(a, b)
     for d, r, i, k in ((d1, r1, i1, k1), (d2, r2, i2, k2)):
-        r = r.cpu().numpy(); k = k.cpu().numpy()
-        assert np.all(d >= r) and rel_err(d, r).max() <= REL_TOL
-        assert (d == r).mean() >= 0.999 and np.array_equal(i[d == r], k[d == r])
+        assert np.array_equal(d, r.cpu().numpy()) and np.array_equal(i, k.cpu().numpy())
     # and the oracle's CUDA-rounding restatement IS the reference kernel, bit for bit
     o1, o2, j1, j2 = native.chamfer_forward(a, b, rounding="cuda")
     assert np.array_equal(o1, r1.cpu().numpy()) and np.array_equal(j1, k1.cpu().numpy())
@@ -135,17 +136,16 @@ def matrix(a, b=None, **kw):
 def test_matrix_against_oracle(P):
     a = sampled_clouds(7, P, 100 + P); b = sampled_clouds(5, P, 200 + P)
     M = matrix(a, b)
-    O = native.pairwise_cd(a, b, rounding="cuda")
-    assert rel_err(M, O).max() <= REL_TOL
+    assert_entries_equal(M, native.pairwise_cd(a, b, rounding="cuda"))
     S = matrix(a)
     assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0)
-    assert rel_err(S, native.pairwise_cd(a, None, rounding="cuda"))[~np.eye(7, dtype=bool)].max() <= REL_TOL
+    assert_entries_equal(S, native.pairwise_cd(a, None, rounding="cuda"))
 
 
 def test_matrix_unequal_point_counts_and_multi_tile():
     a = sampled_clouds(3, 5000, 301); b = sampled_clouds(4, 2500, 302)
     M = matrix(a, b)
-    assert rel_err(M, native.pairwise_cd(a, b, rounding="cuda")).max() <= REL_TOL
+    assert_entries_equal(M, native.pairwise_cd(a, b, rounding="cuda"))
 
 
 @pytest.mark.parametrize("shape", [(3, 4, 5000, 5000), (2, 3, 6000, 4500), (2, 2, 333, 70)])
@@ -163,8 +163,8 @@ def test_matrix_merged_origin_points(shape):
     plain = matrix(a, b, merge_origin=False)
     merged = matrix(a, b, merge_origin=True)
     O = native.pairwise_cd(a, b, rounding="cuda")
-    assert np.all(np.abs(merged - plain) <= 2.0 ** -23 * np.abs(plain))
-    assert np.abs(merged - O).max() <= REL_TOL * O.max()
+    assert np.all(np.abs(merged - plain) <= ULP * np.abs(plain))
+    assert np.all(np.abs(merged - O) <= ULP * np.abs(O)) and np.all(np.abs(plain - O) <= ULP * np.abs(O))
     if pa == pb:
         S0 = matrix(a, merge_origin=False); S1 = matrix(a, merge_origin=True)
         assert np.array_equal(S1, S1.T) and np.all(np.diag(S1) == 0)
@@ -204,8 +204,7 @@ def test_matrix_row_shards_are_bit_identical():
         chamfer_matrix(cuda(a), None, rows=(r, 23, G), compact_rows=True, out=blk)
         parts.append(blk)
     from dusty_gan_b200 import sharding
-    U = sharding.assemble_upper(torch.stack(parts), 23, G)
-    S = sharding.symmetrize_upper(U).cpu().numpy()
+    S = sharding.assemble_symmetric(torch.stack(parts), 23).cpu().numpy()
     assert np.array_equal(S, full)
     b = sampled_clouds(9, 512, 402)
     rect = matrix(a, b)
@@ -229,9 +228,9 @@ def test_matrix_full_size_properties():
     for _ in range(6):
         i, j = rng.integers(0, 1000, 2)
         o = native.pairwise_cd(ref[i:i + 1], gen[j:j + 1], rounding="cuda")[0, 0]
-        assert abs(Mrg[i, j] - o) <= REL_TOL * o
+        assert abs(Mrg[i, j] - o) <= ULP * o
         o = native.pairwise_cd(gen[i:i + 1], gen[j:j + 1], rounding="cuda")[0, 0]
-        assert abs(Mgg[i, j] - o) <= REL_TOL * max(o, 1e-30)
+        assert abs(Mgg[i, j] - o) <= ULP * o
 
 
 def test_forward_against_reference_cuda_golden(golden):
@@ -241,5 +240,4 @@ def test_forward_against_reference_cuda_golden(golden):
         a = sampled_clouds(b, n, seed); c = lidar_like_clouds(b, m, seed + 1)
         d1, d2, i1, i2 = run_forward(a, c)
         for d, r, ix, k in ((d1, g[f"cd{i}_dist1"], i1, g[f"cd{i}_idx1"]), (d2, g[f"cd{i}_dist2"], i2, g[f"cd{i}_idx2"])):
-            assert np.all(d >= r) and rel_err(d, r)[r > 0].max() <= REL_TOL
-            assert (d == r).mean() >= 0.999 and np.array_equal(ix[d == r], k[d == r])
+            assert np.array_equal(d, r) and np.array_equal(ix, k)      # the reference kernel's own output on a B200

@@ -148,3 +148,73 @@ def test_rejects_cpu_and_grad_inputs():
     head = DUSty1(torch.nn.Identity(), tau=1.0)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         head.maskout({"depth": torch.zeros(1, 1, 8, 8), "confidence": torch.zeros(1, 1, 8, 8)})
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_setup_fixed_noise_hook_freezes_the_noise_on_the_fused_heads(kind):
+    """utils.setup(fix_noise=True) registers a forward pre-hook on every GumbelSigmoid that freezes
+    ``fixed_noise`` on the first call (reference utils/__init__.py:141-149). The fused heads never call the
+    gate modules, so they must run those hooks themselves: one noise map for every batch, masks bit-equal to
+    the op chain fed that map."""
+    from dusty_gan_b200.models.dusty import DUSty1, DUSty2, GumbelSigmoid
+    from dusty_gan_b200 import pipeline
+    B, H, W = 4, 64, 512
+    head = (DUSty1 if kind == 1 else DUSty2)(torch.nn.Identity(), tau=1.0).cuda().eval()
+
+    def set_gumbel_noise(m, i):                    # verbatim from the reference's setup()
+        if m.fixed_noise is None:
+            m.fixed_noise = m.logistic_noise(i[0])[[0]]
+
+    for m in head.modules():
+        if isinstance(m, GumbelSigmoid):
+            m.register_forward_pre_hook(set_gumbel_noise)
+    gate = head.gumbel if kind == 1 else head.gumbel_pixel
+    assert gate.fixed_noise is None
+    lidar = make_lidar(H, W)
+    torch.manual_seed(123)
+    outs = []
+    for seed in (1, 2, 3):
+        depth, conf, _, _ = head_inputs(B, kind, H, W, seed, "cuda")
+        if seed == 2:
+            out = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)
+        else:
+            out = head.maskout({"depth": depth, "confidence": conf})
+        noise = gate.fixed_noise
+        assert noise is not None and noise.shape == (1, 1, H, W)
+        outs.append(noise.clone())
+        if kind == 1:
+            mask, dout = hp.maskout_dusty1(depth, conf, noise)
+        else:
+            mask, dout = hp.maskout_dusty2(depth, conf, noise)
+        assert_bit_equal(out["mask"], mask, "mask under the frozen noise")
+        assert_bit_equal(out["depth"], dout, "depth under the frozen noise")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])      # drawn once, reused forever
+    if kind == 2:
+        assert head.gumbel_image.fixed_noise is None       # eval mode never calls the image gate (models/dusty.py:120)
+
+
+def test_inv_to_xyz_and_downsample_are_differentiable_like_the_reference():
+    """demo.py back-propagates a Chamfer loss through lidar.inv_to_xyz and downsample_point_clouds
+    (GatherOperation): the gradients must flow, and match autograd through the reference's op chain."""
+    from dusty_gan_b200.utils.sampling.fps import downsample_point_clouds
+    H, W = 16, 64
+    lidar = make_lidar(H, W)
+    g = torch.Generator().manual_seed(9)
+    inv = torch.rand(2, 1, H, W, generator=g).cuda()
+    inv[:, :, ::3, ::5] = 0.0                                   # dropped pixels
+    x = inv.clone().requires_grad_(True)
+    xyz = lidar.inv_to_xyz(x, tol=0.0)
+    w = torch.randn(xyz.shape, generator=g).cuda()
+    (xyz * w).sum().backward()
+    y = inv.clone().requires_grad_(True)
+    ref = hp.inv_to_xyz(y, lidar.angle, 0.9, 120.0, 0.0)
+    (ref * w).sum().backward()
+    assert torch.allclose(x.grad, y.grad, rtol=1e-4, atol=1e-6)
+    assert bool((x.grad[:, :, ::3, ::5] == 0).all())
+    pts = xyz.detach().flatten(2).transpose(1, 2).contiguous().requires_grad_(True)
+    sub = downsample_point_clouds(pts, 32)
+    assert sub.requires_grad
+    sub.sum().backward()
+    assert pts.grad.sum().item() == pytest.approx(2 * 32 * 3)
+    with torch.no_grad():
+        assert torch.equal(downsample_point_clouds(pts, 32), sub)

@@ -145,3 +145,52 @@ def test_config0_64_vs_64_at_full_size():
     expect = om.scores_from_matrices(O[:N, :N], O[:N, N:], O[N:, N:])
     for k in KEYS:
         assert scores[k] == pytest.approx(expect[k], rel=1e-5, abs=1e-12), k
+
+
+def test_fused_epilogue_scores_are_bit_identical_to_the_matrix_path():
+    """compute_cov_mmd_1nna reduces every entry inside the matrix kernel's epilogue (packed 64-bit minima)
+    instead of storing (Nr+Ng)^2 floats; the scores must be exactly those of matrices + finaliser kernels, for
+    equal point counts (one stacked launch) and unequal ones (three launches), including exact ties."""
+    from dusty_gan_b200.utils.metrics import cov_mmd_1nna as m
+    cases = [(sampled_clouds(37, 512, 81), sampled_clouds(41, 512, 82)),
+             (sampled_clouds(9, 300, 83), sampled_clouds(14, 640, 84)),
+             (sampled_clouds(1, 64, 85), sampled_clouds(1, 64, 86))]
+    dup = sampled_clouds(12, 256, 87)
+    cases.append((dup[[0, 0, 1, 2, 2, 3]], dup[[0, 4, 4, 5, 2, 2, 6]]))          # duplicated clouds: exact ties, zeros
+    for gen, ref in cases:
+        g, r = cuda(gen), cuda(ref)
+        m.FUSED_EPILOGUE = True
+        try:
+            fused = m.compute_cov_mmd_1nna(g, r, 512, ("cd",), verbose=False)
+            m.FUSED_EPILOGUE = False
+            plain = m.compute_cov_mmd_1nna(g, r, 512, ("cd",), verbose=False)
+        finally:
+            m.FUSED_EPILOGUE = True
+        assert fused == plain
+        expect = om.compute_cov_mmd_1nna(gen, ref)
+        for k in KEYS:
+            assert fused[k] == pytest.approx(expect[k], rel=1e-6, abs=1e-12), k
+
+
+def test_fused_evaluation_never_allocates_an_n_by_n_tensor():
+    """configs[3]'s cloud count (5000 vs 5000) at 64 points per cloud: the stacked matrix would be 10000^2 x 4 B
+    = 400 MB (the reference adds a 400 MB diagonal temporary, cov_mmd_1nna.py:82); the fused path may only
+    allocate O(N) scratch on top of the stacked copy of the clouds."""
+    from dusty_gan_b200.utils.metrics import cov_mmd_1nna as m
+    N, P = 5000, 64
+    gen = cuda(sampled_clouds(N, P, 91)); ref = cuda(sampled_clouds(N, P, 92))
+    m.compute_cov_mmd_1nna(gen[:8], ref[:8], 512, ("cd",), verbose=False)          # warm-up: library, context
+    torch.cuda.synchronize(); torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    scores = m.compute_cov_mmd_1nna(gen, ref, 512, ("cd",), verbose=False)
+    torch.cuda.synchronize()
+    extra = torch.cuda.max_memory_allocated() - base
+    clouds_bytes = 2 * N * P * 3 * 4
+    scan_bytes = 2 * N * P * 16
+    assert extra <= clouds_bytes + scan_bytes + (8 << 20), extra        # stacked copy + scan-format copy + 8 MB; no 400 MB matrix
+    m.FUSED_EPILOGUE = False
+    try:
+        plain = m.compute_cov_mmd_1nna(gen, ref, 512, ("cd",), verbose=False)
+    finally:
+        m.FUSED_EPILOGUE = True
+    assert scores == plain

@@ -24,26 +24,23 @@ def test_matrix_point_count_boundaries(pa, pb):
     a = lidar_like_clouds(3, pa, 1000 + pa, dropped=0.2); b = lidar_like_clouds(2, pb, 2000 + pb, dropped=0.2)
     M = chamfer_matrix(cuda(a), cuda(b)).cpu().numpy()
     O = native.pairwise_cd(a, b, rounding="cuda")
-    assert np.abs(M - O).max() <= REL_TOL * max(O.max(), 1e-30), (M, O)
+    assert np.all(np.abs(M - O) <= 2.0 ** -23 * np.abs(O)), (M, O)          # per entry, one ulp
     S = chamfer_matrix(cuda(a)).cpu().numpy()
     Os = native.pairwise_cd(a, None, rounding="cuda")
     assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0)
-    assert np.abs(S - Os).max() <= REL_TOL * max(Os.max(), 1e-30)
+    assert np.all(np.abs(S - Os) <= 2.0 ** -23 * np.abs(Os))
 
 
 @pytest.mark.parametrize("b,n,m", [(1, 1, 1), (1, 33, 7), (2, 256, 257), (3, 513, 100), (5, 1024, 1025), (70, 64, 64),
                                    (2, 2049, 2048), (1, 4100, 9000), (40, 300, 300)])
 def test_batch_forward_shapes(b, n, m):
-    """Batch front end: rows per thread follow the cloud size and the number of CTAs; dist and idx bit-equal
-    to the reference kernel's restatement wherever the candidates are not tied within the search rounding."""
+    """Batch front end: rows per thread follow the cloud size and the number of CTAs; every distance bit-equal
+    to the reference kernel's restatement."""
     from dusty_gan_b200.utils.metrics.distance import chamfer_distance
     a = sampled_clouds(b, n, 31 + n); c = sampled_clouds(b, m, 47 + m)
     d1, d2 = chamfer_distance(cuda(a), cuda(c))
     o1, o2, _, _ = native.chamfer_forward(a, c, rounding="cuda")
-    for got, want in ((d1.cpu().numpy(), o1), (d2.cpu().numpy(), o2)):
-        assert (got == want).mean() >= 0.999
-        assert rel_err(got, want).max() <= 1e-4       # a tie inside the search rounding picks a neighbour: still a reference distance
-        assert got.mean() == pytest.approx(want.mean(), rel=1e-6)
+    assert np.array_equal(d1.cpu().numpy(), o1) and np.array_equal(d2.cpu().numpy(), o2)
 
 
 @pytest.mark.parametrize("n,m,clouds", [(1, 1, 2), (5, 9, 3), (127, 64, 2), (128, 128, 3), (129, 40, 2), (4097, 300, 2), (20000, 700, 150),
