@@ -3,19 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Headline (BASELINE.json): Chamfer pairs/sec. Workload = configs[2]: 1000 vs 1000 clouds of 2048
+Headline (BASELINE.json): Chamfer pairs/sec. Default workload = configs[2]: 1000 vs 1000 clouds of 2048
 FPS-sampled points, full MMD/COV/1-NNA. One "step" is one complete evaluation through the public
-API ``compute_cov_mmd_1nna(gen, ref, 512, ("cd",))``: the three matrices M_rr, M_rg, M_gg
-(3 N^2 = 3 000 000 entries, each a bidirectional Chamfer distance) plus the scores.
+API ``compute_cov_mmd_1nna(gen, ref, 512, ("cd",))``: the entries of M_rr, M_rg, M_gg
+(3 N^2 = 3 000 000, each a bidirectional Chamfer distance) reduced to the scores.
   value   entries/s with the clouds resident in HBM (device-timed, max over ranks)
   e2e     the same call fed from pinned HOST buffers: H2D copy of both cloud sets + evaluation + D2H
           of the scores inside the timed region
-  roofline   the Chamfer kernel against the FP32 FFMA peak (algorithmic AND executed flops)
-  stages  configs[1] (head + projection, batch 256 of 64x512, HBM roofline) and range image -> FPS
-          clouds/s, measured in the same run
+  roofline   the Chamfer kernel against the FP32 FFMA peak; ``frac`` counts the flops the kernel EXECUTES
+          (upper triangle of the stacked matrix), ``frac_algorithmic`` the 3 N^2 entries the reference fills
+  stages  configs[1] (head + projection, batch 256 of 64x512, HBM roofline, with and without compaction),
+          FPS at 888 / 148 / 32 clouds, scan preprocessing, JSD -- compact numbers; the long form goes to stderr
   cpu_baseline   the reference's own compiled CPU path (oracle/_ref) on a bounded sample
+--workload cfg3 | cfg4 select BASELINE configs[3] (DUSty-II, 5000 vs 5000 x 2048) and configs[4] (500 vs 500
+un-sampled 32 768-point clouds); they are meant for --gpus 8.
 With --gpus N > 1 (launched under torchrun) the rows of the stacked matrix are dealt cyclically to
-the ranks and combined by one all-gather; total work is fixed, so scaling is "strong".
+the ranks and the per-cloud (min, arg-min) vectors are combined by one all-gather; total work is fixed, so
+scaling is "strong".
 """
 import argparse
 import json
@@ -31,10 +35,19 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if "DUSTY_NCCL_DEBUG" in os.environ:
-    os.environ["NCCL_DEBUG"] = os.environ["DUSTY_NCCL_DEBUG"]
-else:
-    os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version banner on stdout; keep stdout to the one JSON line
+# NCCL's INFO log proves how many ranks the communicator really has. It goes to stdout by default, which must
+# carry only the one JSON line: unless the caller chose a file, every rank logs to its own file and rank 0
+# copies the communicator lines to stderr and into the JSON line ("comm").
+NCCL_LOG = None
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    if "NCCL_DEBUG_FILE" not in os.environ:
+        NCCL_LOG = f"/tmp/dusty_nccl_{os.environ.get('MASTER_PORT', '0')}_rank{os.environ.get('RANK', '0')}.log"
+        os.environ["NCCL_DEBUG_FILE"] = NCCL_LOG
+        try:
+            os.remove(NCCL_LOG)
+        except OSError:
+            pass
 
 N_CLOUDS = 1000          # per set (configs[2])
 N_POINTS = 2048
@@ -165,65 +178,117 @@ def time_events(fn, iters, warmup, flush=None):
     return ms
 
 
-def bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz=1965.0):
-    """configs[1] and the range-image -> FPS stage on one GPU."""
+WORKLOADS = {       # BASELINE.json configs[2..4]: (clouds per set, head, un-sampled)
+    "cfg2": (1000, 1, False),
+    "cfg3": (5000, 2, False),
+    "cfg4": (500, 1, True),
+}
+
+
+def resolve_workload(args):
+    """(N, head kind, un-sampled, points per cloud, the config.workload string both arms print)."""
+    N, kind, full_res = WORKLOADS[args.workload]
+    N = args.clouds if args.clouds is not None else N
+    kind = args.dusty if args.dusty is not None else kind
+    full_res = full_res or args.full_resolution
+    P = H * W if full_res else N_POINTS
+    names = {"cfg2": "configs[2]", "cfg3": "configs[3]", "cfg4": "configs[4]"}
+    text = (f"{names[args.workload]}: {N} vs {N} clouds x {P} points (DUSty-{'II' if kind == 2 else 'I'} head, "
+            f"{'un-sampled' if full_res else 'FPS'}), full MMD/COV/1-NNA via Chamfer")
+    return N, kind, full_res, P, text
+
+
+def r4(x):
+    """Five significant digits: keeps the one JSON line short enough for the driver's tail."""
+    if isinstance(x, float):
+        return float(f"{x:.5g}")
+    if isinstance(x, dict):
+        return {k: r4(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [r4(v) for v in x]
+    return x
+
+
+def bench_head(device, hbm_gbs, kind, compact):
+    """configs[1]: batch 256 of 64x512 through the fused head + projection. 20 launches replayed as one CUDA
+    graph (a single launch is latency dominated) that rotate over 4 independent input AND output
+    buffer sets: 4 x 67/101 MB of inputs alone exceed the 126 MB L2, so no launch finds its inputs cached."""
+    from dusty_gan_b200 import _lib, pipeline
+    lidar = make_lidar(device)
+    head = make_head(kind, device)
+    nsets, reps = 4, 20
+    sets = []
+    lib = _lib.load()
+    for i in range(nsets):
+        depth, conf = backbone_like(HEAD_BATCH, kind, 11 + i, device)
+        bufs = {"mask": torch.empty_like(conf), "depth": torch.empty_like(depth),
+                "points": torch.empty(HEAD_BATCH, H * W, 3, device=device)}
+        if compact:
+            bufs.update(valid_count=torch.empty(HEAD_BATCH, device=device, dtype=torch.int32),
+                        valid_index=torch.empty(HEAD_BATCH, H * W, device=device, dtype=torch.int32),
+                        valid_points=torch.empty(HEAD_BATCH, H * W, 3, device=device),
+                        workspace=_lib.workspace(lib.dusty_head_project_workspace_bytes(HEAD_BATCH, H, W), device))
+        sets.append((depth, conf, bufs))
+
+    def run(i=0):
+        depth, conf, bufs = sets[i % nsets]
+        return pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0, compact=compact, buffers=bufs)
+    out = run()
+    torch.cuda.synchronize()
+    valid_frac = float(out["valid_count"].float().mean()) / (H * W) if compact else None
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(reps):
+                run(i)
+    t = statistics.median(time_events(graph.replay, 5, 2)) * 1e-3 / reps
+    px = HEAD_BATCH * H * W
+    bytes_alg = px * (28 if kind == 1 else 36)
+    res = {"ms": t * 1e3, "images_per_s": HEAD_BATCH / t, "gbs": bytes_alg / t / 1e9, "frac": bytes_alg / t / 1e9 / hbm_gbs}
+    if compact:     # index map + compacted xyz of the valid pixels: real traffic, not algorithmic bytes (SURVEY.md 8d)
+        moved = bytes_alg + px * valid_frac * 16
+        res.update(valid_frac=valid_frac, gbs_moved=moved / t / 1e9, frac_moved=moved / t / 1e9 / hbm_gbs)
+    return res
+
+
+def bench_fps(device, head, lidar, sm_max_mhz):
     from dusty_gan_b200 import pipeline
+    from dusty_gan_b200.utils.sampling.fps import downsample_point_clouds
+    n_fps = 888                                   # six clouds per SM: the throughput variant of the FPS kernel
+    depth, conf = backbone_like(n_fps, 1, 12, device)
+    pts = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"]
+    elig = ((pts.double() ** 2).sum(-1) > 1e-3).sum(1).float()
+    res = {"points_in": H * W, "points_out": N_POINTS, "eligible_mean": float(elig.mean()), "eligible_max": float(elig.max())}
+    for n in (n_fps, 148, 32):                    # 32 = the reference's batch (evaluate_synthesis.py:152-157)
+        sub = pts[:n].contiguous()
+        t = statistics.median(time_events(lambda: downsample_point_clouds(sub, N_POINTS), 5, 2)) * 1e-3
+        res[f"clouds_per_s_b{n}"] = n / t
+        res[f"ms_b{n}"] = t * 1e3
+    # a real-KITTI-like cloud: ~28 k eligible points (more than fit one SM's shared memory)
+    dense = pts[:148].clone()
+    zero = (dense == 0).all(-1)
+    filler = torch.roll(dense, 1, 0)
+    dense[zero] = filler[zero] * 1.01
+    e2 = ((dense.double() ** 2).sum(-1) > 1e-3).sum(1).float()
+    t = statistics.median(time_events(lambda: downsample_point_clouds(dense, N_POINTS), 5, 2)) * 1e-3
+    res["dense_eligible_mean"] = float(e2.mean())
+    res["clouds_per_s_dense_b148"] = 148 / t
+    t = statistics.median(time_events(lambda: pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, N_POINTS, tol=0.0), 3, 1)) * 1e-3
+    res["image_to_cloud_per_s_b888"] = n_fps / t
+    return res, depth, conf, pts
+
+
+def bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz=1965.0):
+    """configs[1], range image -> FPS, the real-data side and JSD on one GPU. Returns (compact, verbose)."""
     from dusty_gan_b200.utils.sampling.fps import downsample_point_clouds
     lidar = make_lidar(device)
     res = {}
     for kind in (1, 2):
-        head = make_head(kind, device)
-        depth, conf = backbone_like(HEAD_BATCH, kind, 11, device)
-        bufs = {"mask": torch.empty_like(conf), "depth": torch.empty_like(depth),
-                "points": torch.empty(HEAD_BATCH, H * W, 3, device=device)}
-
-        def run():
-            pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0, buffers=bufs)
-        run()
-        torch.cuda.synchronize()
-        # 20 back-to-back launches replayed as one CUDA graph: a single launch is latency dominated
-        # (SURVEY.md 8d). Inputs + outputs are 235/302 MB per launch, larger than the 126 MB L2.
-        reps = 20
-        side = torch.cuda.Stream()
-        with torch.cuda.stream(side):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                for _ in range(reps):
-                    run()
-        ms = time_events(graph.replay, 5, 2)
-        t = statistics.median(ms) * 1e-3 / reps
-        api_ms = statistics.median(time_events(run, 10, 3, flush))
-        bytes_alg = HEAD_BATCH * H * W * (28 if kind == 1 else 36)
-        res[f"head_project_dusty{kind}"] = {
-            "images_per_s": HEAD_BATCH / t, "ms": t * 1e3, "single_api_call_ms": api_ms,
-            "roofline": {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": hbm_gbs, "unit": "GB/s",
-                         "frac": bytes_alg / t / 1e9 / hbm_gbs, "peak_source": peak_src,
-                         "algorithmic_bytes": bytes_alg,
-                         "traffic": ncu_traffic("head_project_dusty1_b256") if kind == 1 else None},
-            "note": f"configs[1]: batch {HEAD_BATCH} of {H}x{W}; {reps} launches replayed as a CUDA graph, outputs preallocated; "
-                    "working set per launch exceeds L2"}
+        res[f"head_dusty{kind}"] = bench_head(device, hbm_gbs, kind, compact=False)
+        res[f"head_dusty{kind}_compact"] = bench_head(device, hbm_gbs, kind, compact=True)
     head = make_head(1, device)
-    n_fps = 888                                   # six clouds per SM: the throughput variant of the FPS kernel
-    depth, conf = backbone_like(n_fps, 1, 12, device)
-    pts = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"]
-    mag = (pts.double() ** 2).sum(-1)
-    elig = (mag > 1e-3).sum(1).float()
-    ms = time_events(lambda: downsample_point_clouds(pts, N_POINTS), 3, 1)
-    t = statistics.median(ms) * 1e-3
-    res["fps"] = {"clouds_per_s": n_fps / t, "ms": t * 1e3, "clouds": n_fps, "points_in": H * W, "points_out": N_POINTS,
-                  "eligible_mean": float(elig.mean()), "eligible_max": float(elig.max()),
-                  "nominal_updates_per_s": float(elig.sum()) * (N_POINTS - 1) / t,
-                  # SURVEY.md 8d: ceilings of an un-pruned kernel, per eligible-point update
-                  "ceilings_updates_per_s": {"shared_memory_12B_per_update": SM_COUNT * 128 * sm_max_mhz * 1e6 / 12,
-                                             "fp32_issue_8_ops_per_update": SM_COUNT * FP32_LANES * sm_max_mhz * 1e6 / 8},
-                  "note": "nominal = eligible points x (samples-1); the pruned kernel skips buckets whose lower bound rules out a "
-                          "change (about 94 % of them), which is how the nominal rate exceeds both ceilings of a kernel that "
-                          "touches every point every iteration; the kernel itself is latency bound (profiles/SUMMARY_r1.md)"}
-
-    def img2cloud():
-        pipeline.generate_points(head, {"depth": depth, "confidence": conf}, lidar, N_POINTS, tol=0.0)
-    ms = time_events(img2cloud, 3, 1)
-    res["range_image_to_fps_clouds_per_s"] = n_fps / (statistics.median(ms) * 1e-3)
+    res["fps"], depth, conf, pts = bench_fps(device, head, lidar, sm_max_mhz)
     res.update(bench_real_side(device, hbm_gbs, peak_src))
     # JSD of the two occupancy histograms (next row 8f-2) on 1000 vs 1000 sampled clouds, as
     # evaluate_synthesis.py:174-177 calls it (clouds halved into the unit sphere)
@@ -232,13 +297,19 @@ def bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz=1965.0):
     ja, jb = sampled[:444].repeat(3, 1, 1)[:1000].contiguous(), sampled[444:].repeat(3, 1, 1)[:1000].contiguous()
     compute_jsd(ja, jb)
     ms = statistics.median(time_events(lambda: compute_jsd(ja, jb), 5, 1))
-    res["jsd"] = {"clouds_per_s": 2000 / (ms * 1e-3), "ms": ms, "clouds": 2000, "points": N_POINTS, "grid": "28^3 in-sphere (9261 cells)",
-                  "note": "two voting launches + one reduction, including the 4-byte read-back of the score"}
+    res["jsd"] = {"clouds_per_s": 2000 / (ms * 1e-3), "ms": ms}
     try:
         stage_cpu_baselines(res, head, lidar, depth[:32], conf[:32], pts[:2], sampled[:4])
     except Exception as exc:        # the checker is optional for the measurement
-        res["cpu_baselines_error"] = repr(exc)[:200]
-    return res
+        res["cpu_error"] = repr(exc)[:120]
+    notes = {
+        "head": f"batch {HEAD_BATCH} of {H}x{W}; 20 launches replayed as a CUDA graph over 4 rotating input+output buffer sets "
+                "(inputs alone 4 x 67/101 MB > 126 MB L2); algorithmic bytes 28/36 B/px (SURVEY.md 8d); *_compact also writes "
+                "valid_count / valid_index / valid_points (frac_moved counts them)",
+        "fps": "32 768 -> 2048 points; b888 = six clouds per SM, b32 = the reference's batch; dense = ~28 k eligible points per cloud",
+        "scan": "256 raw scans 64x2048x4 -> inv/mask/points, 10 back-to-back calls, 512 MB of input > L2",
+        "peak": f"HBM {hbm_gbs} GB/s {peak_src}"}
+    return res, notes
 
 
 def stage_cpu_baselines(res, head, lidar, depth, conf, pts, jsd_clouds):
@@ -255,31 +326,20 @@ def stage_cpu_baselines(res, head, lidar, depth, conf, pts, jsd_clouds):
         return hp.project_2d_to_3d_dense(dout, angle, 0.9, 120.0, 0.0)
     head_cpu()
     t0 = time.perf_counter(); head_cpu(); dt = time.perf_counter() - t0
-    res["head_project_dusty1"]["cpu_baseline"] = {
-        "value": len(d) / dt, "unit": "images/s", "cores": threads, "kind": "port",
-        "sample": f"{len(d)} images of {H}x{W} through the reference's ATen op chain (models/dusty.py:45-91, "
-                  f"utils/lidar.py:38-68) on CPU, {threads} torch threads"}
+    res["cpu"] = {"head_images_per_s": len(d) / dt, "head_cores": threads}
     p = pts.cpu().numpy()
     t0 = time.perf_counter(); native.fps(p, N_POINTS); dt = time.perf_counter() - t0
-    res["fps"]["cpu_baseline"] = {
-        "value": len(p) / dt, "unit": "clouds/s", "cores": 1, "kind": "port",
-        "sample": f"{len(p)} clouds of {H * W} points -> {N_POINTS}: oracle's single-thread C replay of the reference "
-                  "CUDA kernel (the reference has no CPU FPS)"}
+    res["cpu"]["fps_clouds_per_s_1core"] = len(p) / dt
     jc = jsd_clouds.cpu().numpy()
     t0 = time.perf_counter(); ojsd.vote(jc); dt = time.perf_counter() - t0
-    res["jsd"]["cpu_baseline"] = {
-        "value": len(jc) / dt, "unit": "clouds/s", "cores": 1, "kind": "port",
-        "sample": f"{len(jc)} clouds x {jc.shape[1]} points: brute-force arg-min against the 9261 grid points "
-                  "(reference utils/metrics/jsd.py:42-84) in numpy"}
+    res["cpu"]["jsd_clouds_per_s_1core"] = len(jc) / dt
     scans = rd.synthetic_scans(4, seed=1)
     t0 = time.perf_counter()
     items = [rd.dataset_item(x, (H, W)) for x in scans]
     rd.preprocess_reals({k: torch.stack([it[k] for it in items]) for k in items[0]})
     dt = time.perf_counter() - t0
-    res[f"scan_preprocess_w{W}"]["cpu_baseline"] = {
-        "value": len(scans) / dt, "unit": "scans/s", "cores": 1, "kind": "port",
-        "sample": f"{len(scans)} scans: numpy dataset preprocess + nearest resize (datasets/kitti.py:54-78; one DataLoader "
-                  "worker's share) and preprocess_reals' torch ops on CPU"}
+    res["cpu"]["scan_per_s_1core"] = len(scans) / dt
+    res["cpu"]["kind"] = "port: oracle restatements of the reference's CPU op chains (it has no CPU FPS)"
 
 
 def bench_real_side(device, hbm_gbs, peak_src):
@@ -306,13 +366,8 @@ def bench_real_side(device, hbm_gbs, peak_src):
         ms = statistics.median(time_events(run, 5, 2)) / reps
         # algorithmic bytes per output pixel: one (x,y,z,reflectance) source point in, inv + mask + xyz out
         bytes_alg = n * H * w_out * (16 + 4 + 4 + 12)
-        res[f"scan_preprocess_w{w_out}"] = {
-            "scans_per_s": n / (ms * 1e-3), "ms": ms, "scans": n,
-            "roofline": {"bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": hbm_gbs, "unit": "GB/s",
-                         "frac": bytes_alg / ms / 1e6 / hbm_gbs, "peak_source": peak_src, "algorithmic_bytes": bytes_alg},
-            "note": f"{n} scans of 64x2048x4 -> 64x{w_out} (nearest), {reps} back-to-back API calls, outputs preallocated, "
-                    f"working set {n * 2} MB in > L2; "
-                    + ("every 4th source point is read: sectors are half used" if w_out != 2048 else "every source point is read")}
+        res[f"scan_w{w_out}"] = {"scans_per_s": n / (ms * 1e-3), "ms": ms, "gbs": bytes_alg / ms / 1e6,
+                                 "frac": bytes_alg / ms / 1e6 / hbm_gbs}
     return res
 
 
@@ -361,46 +416,70 @@ def cpu_reference_sample(a, b, rows, cols, variant, procs):
 
 # ---------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (nnsearch, cd/chamfer_distance.cpp:39-62, compiled -O3
+    from /root/reference sources into oracle/_ref) on all host cores, on a bounded sample of the SAME workload:
+    the same cloud statistics and points per cloud; brute-force nnsearch does the same work for every entry, so
+    entries/s of the sample is entries/s of the whole matrix."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rng_a = synthetic_cpu_clouds(max(64, os.cpu_count() or 1), 1); rng_b = synthetic_cpu_clouds(64, 2)
+    N, kind, full_res, P, workload_text = resolve_workload(args)
     cores = os.cpu_count() or 1
     rows = max(cores, 16)
-    cols = 64          # 16 x 64 = 1024 entries (~1-4 s per step on 16-8 cores)
+    cols = 64 if P <= 4096 else 2     # ~1-4 s per step
+    if P > 4096:
+        rows = max(cores // 2, 2)
+    rng_a = synthetic_cpu_clouds(rows, 1, P, full_res); rng_b = synthetic_cpu_clouds(cols, 2, P, full_res)
     vals = []
     t_all = time.perf_counter()
-    kind = "reference"
+    kind_ = "reference"
     for s in range(args.warmup + args.steps):
         if s >= 1 and time.perf_counter() - t_all > 150:      # keep the whole arm within a few minutes
             break
-        v, dt, kind = cpu_reference_sample(rng_a, rng_b, rows, cols, "dustyref_cd_o3", cores)
+        v, dt, kind_ = cpu_reference_sample(rng_a, rng_b, rows, cols, "dustyref_cd_o3", cores)
         if s >= args.warmup or args.warmup + args.steps <= 1:
             vals.append((v, dt))
     if not vals:
         vals.append((v, dt))
     value = statistics.mean(v for v, _ in vals)
     ms = statistics.mean(dt for _, dt in vals) * 1e3
-    sample = (f"{rows}x{cols} entries of the 1000x1000x3 workload per step, P={N_POINTS}; reference nnsearch "
-              f"(cd/chamfer_distance.cpp:39-62) compiled -O3 from /root/reference sources, rows over {cores} processes")
-    print(json.dumps({
+    sample = (f"{rows}x{cols} entries per step of the {N}x{N}x3 entries of this workload, P={P}; reference nnsearch "
+              f"(cd/chamfer_distance.cpp:39-62) compiled -O3 from the reference sources, rows over {cores} processes")
+    print(json.dumps(r4({
         "impl": "reference", "metric": "chamfer_pairs_per_s", "value": value, "unit": "entries/s", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: 1000 vs 1000 clouds x 2048 pts, MMD/COV/1-NNA via Chamfer (bounded sample)",
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": workload_text, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind_, "sample": sample},
         "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})))
 
 
-def synthetic_cpu_clouds(n, seed):
-    """Host-side clouds with the same statistics as the GPU-made ones (only used by the CPU arm when no
-    GPU is involved): sampled LiDAR-like points, sensor-centred, normalised range."""
+def synthetic_cpu_clouds(n, seed, points=N_POINTS, dropped=False):
+    """Host-side clouds with the same statistics as the GPU-made ones (only used by the CPU arm, which must not
+    touch the GPU kernels): LiDAR-like points, sensor-centred, normalised range; un-sampled clouds keep half of
+    their points at the origin (dropped pixels)."""
     rng = np.random.default_rng(seed)
-    az = rng.uniform(-np.pi, np.pi, (n, N_POINTS)); el = np.deg2rad(rng.uniform(-24.8, 2.0, (n, N_POINTS)))
-    r = np.exp(rng.uniform(np.log(0.035), np.log(0.7), (n, N_POINTS)))
+    az = rng.uniform(-np.pi, np.pi, (n, points)); el = np.deg2rad(rng.uniform(-24.8, 2.0, (n, points)))
+    r = np.exp(rng.uniform(np.log(0.035), np.log(0.7), (n, points)))
+    if dropped:
+        r = np.where(rng.uniform(size=r.shape) < 0.5, 0.0, r)
     return np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)], -1).astype(np.float32)
+
+
+
+
+def nccl_comm_evidence(world):
+    """Communicator lines of rank 0's NCCL INFO log: the driver's rank check reads 'nranks N' from them."""
+    if NCCL_LOG is None or not os.path.exists(NCCL_LOG):
+        return {"backend": "nccl", "world_size": world, "log": os.environ.get("NCCL_DEBUG_FILE")}
+    with open(NCCL_LOG, errors="replace") as fh:
+        lines = [ln.strip() for ln in fh if "nranks" in ln]
+    import re
+    seen = sorted({int(m.group(1)) for ln in lines for m in [re.search(r"nranks (\d+)", ln)] if m})
+    for ln in lines[:4]:
+        log("[nccl] " + ln)
+    return {"backend": "nccl", "world_size": world, "nranks_seen": seen, "init_line": (lines[-1][-160:] if lines else None)}
 
 
 def main():
@@ -409,10 +488,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clouds", type=int, default=N_CLOUDS, help="clouds per set (default = configs[2])")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json configs[2] (default), [3] or [4]")
+    ap.add_argument("--clouds", type=int, default=None, help="clouds per set (default: the workload's)")
     ap.add_argument("--skip-extras", action="store_true", help="headline only (no stages / cpu baseline)")
-    ap.add_argument("--dusty", type=int, default=1, choices=[1, 2], help="head that makes the clouds (configs[3] uses DUSty-II)")
-    ap.add_argument("--full-resolution", action="store_true", help="configs[4]: un-sampled 64x512 clouds (32768 points each)")
+    ap.add_argument("--dusty", type=int, default=None, choices=[1, 2], help="head that makes the clouds (default: the workload's)")
+    ap.add_argument("--full-resolution", action="store_true", help="un-sampled 64x512 clouds (32768 points each), as cfg4")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -430,12 +510,11 @@ def main():
     from dusty_gan_b200 import _lib
     from dusty_gan_b200.utils.metrics import cov_mmd_1nna as M
     hbm_gbs, sm_max_mhz, peak_src = peaks()
-    N = args.clouds
-    lidar = make_lidar(device); head = make_head(args.dusty, device)
-    P = H * W if args.full_resolution else N_POINTS
+    N, kind, full_res, P, workload_text = resolve_workload(args)
+    lidar = make_lidar(device); head = make_head(kind, device)
     t0 = time.perf_counter()
-    ref = make_clouds(N, 2, head, lidar, device, args.dusty, args.full_resolution)
-    gen = make_clouds(N, 1, head, lidar, device, args.dusty, args.full_resolution)
+    ref = make_clouds(N, 2, head, lidar, device, kind, full_res)
+    gen = make_clouds(N, 1, head, lidar, device, kind, full_res)
     torch.cuda.synchronize()
     log(f"[rank {rank}] inputs ready in {time.perf_counter() - t0:.1f}s: 2 x {tuple(ref.shape)}")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
@@ -507,14 +586,12 @@ def main():
     exe_entries = (2 * N) * (2 * N + 1) / 2                                 # stacked upper triangle incl. diagonal
     exe_flops = exe_entries * flops_per_entry / world
     merged = None
-    if args.full_resolution:
+    if full_res:
         # un-sampled clouds: every cloud's (0,0,0) points are scanned as one weighted point
         # (DUSTY_MATRIX_MERGE_ORIGIN), so the executed pair count is data dependent: count it
         kept = torch.cat([(c != 0).any(-1).sum(1) + ((c == 0).all(-1).any(1)).long() for c in (ref, gen)]).double()
         exe_flops = 12.0 * float((kept.sum() ** 2 + (kept ** 2).sum()) / 2) / world
-        merged = {"points_kept_mean": float(kept.mean()), "points_per_cloud": P,
-                  "note": "kept points are spatially sorted and chunks are pruned by box distance (exact): the executed pair count is "
-                          "data dependent and not counted by the kernel, so 'executed' below is an upper bound (every kept pair)"}
+        merged = {"points_kept_mean": float(kept.mean()), "points_per_cloud": P, "pruned": True}
     peak_nominal = SM_COUNT * FP32_LANES * 2 * sm_max_mhz * 1e6 / 1e12
     sink = torch.zeros(1, device=device)
     import ctypes as C
@@ -525,51 +602,52 @@ def main():
         _lib.check(lib.dusty_probe_fp32_peak(64, _lib.ptr(sink), C.byref(flops), _lib.stream_of(sink)), "probe")
     probe_ms = min(time_events(probe, 5, 2))
     peak_probe = flops.value / (probe_ms * 1e-3) / 1e12
+    exe_rate = exe_flops / (kern_ms * 1e-3) / 1e12
+    alg_rate = alg_flops / (kern_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "fp32_ffma", "kernel": "dusty::chamfer::nn_kernel<8,true>", "points_per_cloud": P,
-        "achieved": alg_flops / (kern_ms * 1e-3) / 1e12, "peak": peak_nominal, "unit": "TFLOP/s",
-        "frac": alg_flops / (kern_ms * 1e-3) / 1e12 / peak_nominal,
-        "executed": exe_flops / (kern_ms * 1e-3) / 1e12, "executed_frac": exe_flops / (kern_ms * 1e-3) / 1e12 / peak_nominal,
-        "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json holds no FP32 figure)",
+        "bound": "fp32_ffma", "kernel": "dusty::chamfer::nn_kernel", "achieved": exe_rate, "peak": peak_nominal, "unit": "TFLOP/s",
+        "frac": exe_rate / peak_nominal, "achieved_algorithmic": alg_rate, "frac_algorithmic": alg_rate / peak_nominal,
+        "peak_source": f"nominal 148x128x2x{sm_max_mhz:.0f} MHz (no FP32 figure in MEASURED_PEAKS.json)",
         "peak_probe_ffma_only": peak_probe, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step,
-        "algorithmic_flops_per_entry": flops_per_entry, "entries_per_launch_algorithmic": entries / world,
-        "entries_per_launch_executed": exe_entries / world, "merged_origin": merged,
-        "traffic": ncu_traffic("chamfer_nn_kernel_n1000") if (world == 1 and N == N_CLOUDS) else None,
-        "note": "algorithmic = 3 N^2 entries x 12 P^2 flop (what the reference fills); executed = stacked upper triangle "
-                "(M_rr and M_gg are symmetric, SURVEY.md S8), same 12 P^2 flop per entry"}
-
+        "flops_per_entry": flops_per_entry, "entries_per_launch_executed": exe_entries / world,
+        "entries_per_launch_algorithmic": entries / world, "merged_origin": merged,
+        "traffic": ncu_traffic("chamfer_nn_kernel_n1000") if (world == 1 and args.workload == "cfg2" and N == N_CLOUDS) else None,
+        "note": "frac = flops executed (upper triangle of the stacked matrix, 12 P^2 per entry; with merged_origin every kept pair, an "
+                "upper bound under pruning); frac_algorithmic = the 3 N^2 entries the reference fills"}
     line = {
         "metric": "chamfer_pairs_per_s", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"configs[2]: {N} vs {N} clouds x {N_POINTS} FPS points, full MMD/COV/1-NNA via Chamfer"
-                                if (N == N_CLOUDS and args.dusty == 1 and not args.full_resolution) else
-                                f"{N} vs {N} clouds x {P} points (DUSty-{'II' if args.dusty == 2 else 'I'} head"
-                                f"{', un-sampled' if args.full_resolution else ', FPS'}), full MMD/COV/1-NNA via Chamfer"),
-                   "entries_per_step": entries, "clouds_from": "synthetic 64x512 range images -> head+projection+FPS kernels",
-                   "parallelism": f"row-sharded x{world}, one all-gather" if world > 1 else "single GPU",
-                   "l2": "256 MB buffer written between timed steps (inputs 49 MB + 64 MB scan copies < 126 MB L2)"},
+        "config": {"workload": workload_text, "entries_per_step": entries, "clouds_from": "synthetic 64x512 range images -> head+projection+FPS kernels",
+                   "parallelism": f"row-sharded x{world}, one all-gather of per-cloud (min, arg-min) keys ({24 * 2 * N} B per rank)" if world > 1 else "single GPU",
+                   "l2": "256 MB buffer written between timed steps"},
         "e2e": {"value": e2e_value, "unit": "entries/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(h_gen.numel() + h_ref.numel()) * 4, "d2h_bytes_per_step": 28},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "scores": {k: scores[k] for k in ("mmd-cd", "cov-cd", "1-nn-accuracy-cd")},
     }
+    if world > 1:
+        line["comm"] = nccl_comm_evidence(world)
     assert e2e_scores == scores, "host-fed and resident runs must agree exactly"
 
     if world == 1 and not args.skip_extras:
         try:
-            line["stages"] = bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz)
+            stages, notes = bench_stages(device, hbm_gbs, peak_src, flush, sm_max_mhz)
+            line["stages"] = stages
+            log("[stages] " + json.dumps({"stages": stages, "notes": notes}))
         except Exception as exc:  # the headline line must still be printed
             line["stages"] = {"error": repr(exc)[:300]}
         # bounded CPU sample: 16 x 16 entries of this very workload through the reference as shipped
         a = ref[:16].cpu().numpy(); b = gen[:16].cpu().numpy()
-        v, dt, kind = cpu_reference_sample(a, b, 16, 16, "dustyref_cd", 1)
+        if full_res:
+            a, b = a[:2], b[:2]
+        v, dt, kind_ = cpu_reference_sample(a, b, len(a), len(b), "dustyref_cd", 1)
         line["cpu_baseline"] = {
-            "value": v, "unit": "entries/s", "cores": 1, "kind": kind, "seconds": dt,
-            "sample": "16 x 16 entries of M_rg of this workload (P=2048) through the reference's nnsearch as shipped "
-                      "(load() passes no flags => g++ -O0, single thread); see --impl reference for the -O3 all-core arm",
+            "value": v, "unit": "entries/s", "cores": 1, "kind": kind_, "seconds": dt,
+            "sample": f"{len(a)} x {len(b)} entries of M_rg of this workload (P={P}) through the reference's nnsearch as shipped "
+                      "(load() passes no flags => g++ -O0, single thread); --impl reference is the -O3 all-core arm",
             "host_cores_available": os.cpu_count()}
-    print(json.dumps(line))
+    print(json.dumps(r4(line)))
     if world > 1:
         dist.destroy_process_group()
 

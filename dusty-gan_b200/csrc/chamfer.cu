@@ -684,28 +684,64 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
   if (tid == 0) meta[c] = make_int2(kept, zeros > 0 ? zeros : 1);
 }
 
-// Reference ChamferDistanceGradKernel (chamfer_distance.cu:148-172): own-term stores plus
-// scatter-adds through the arg-min indices.
-__global__ void __launch_bounds__(256) grad_kernel(int b, int n, const float* __restrict__ xyz1, int m,
-                                                   const float* __restrict__ xyz2, const float* __restrict__ gd1,
-                                                   const int* __restrict__ idx1, float* __restrict__ g1,
-                                                   float* __restrict__ g2) {
-  const long long total = (long long)b * n;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const long long i = e / n;
-    const int j2 = idx1[e];
-    const float* a = xyz1 + e * 3;
-    const float* c = xyz2 + (i * m + j2) * 3;
-    const float g = gd1[e] * 2.0f;
-    const float gx = g * (a[0] - c[0]), gy = g * (a[1] - c[1]), gz = g * (a[2] - c[2]);
-    atomicAdd(g1 + e * 3 + 0, gx);
-    atomicAdd(g1 + e * 3 + 1, gy);
-    atomicAdd(g1 + e * 3 + 2, gz);
-    float* o = g2 + (i * m + j2) * 3;
-    atomicAdd(o + 0, -gx);
-    atomicAdd(o + 1, -gy);
-    atomicAdd(o + 2, -gz);
+// Reference ChamferDistanceGradKernel (chamfer_distance.cu:148-190): after two memsets, every point adds
+// 2 g (p - q) to its own gradient and subtracts it from its nearest neighbour's, all with atomicAdd, one launch
+// per direction. Here every gradient element is WRITTEN once by the thread that owns the point (its own term, a
+// plain 128-bit-friendly store: no memset, no atomic), then one more launch adds the neighbour terms of both
+// directions; lanes of a warp that hit the same neighbour are summed in registers first (ordered clouds send
+// runs of consecutive points to the same neighbour), so one RED per distinct target leaves the warp.
+struct GradArgs {
+  int b, n, m;
+  const float* xyz1; const float* xyz2;
+  const float* gd1; const float* gd2;
+  const int* idx1; const int* idx2;
+  float* g1; float* g2;
+};
+
+// element e of the concatenation [cloud set 1 | cloud set 2] -> (own point, neighbour, 2 g, target slot)
+__device__ __forceinline__ bool grad_term(const GradArgs& a, long long e, float (&t)[3], long long& own, long long& nbr, bool& second) {
+  const long long n1 = (long long)a.b * a.n, n2 = (long long)a.b * a.m;
+  if (e >= n1 + n2) return false;
+  second = e >= n1;
+  const long long k = second ? e - n1 : e;
+  const int cnt = second ? a.m : a.n, other = second ? a.n : a.m;
+  const long long i = k / cnt;
+  const int j = (second ? a.idx2 : a.idx1)[k];
+  const float* p = (second ? a.xyz2 : a.xyz1) + k * 3;
+  nbr = i * other + j;
+  const float* q = (second ? a.xyz1 : a.xyz2) + nbr * 3;
+  const float g = (second ? a.gd2 : a.gd1)[k] * 2.0f;
+  t[0] = g * (p[0] - q[0]); t[1] = g * (p[1] - q[1]); t[2] = g * (p[2] - q[2]);
+  own = k;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) grad_own_kernel(const GradArgs a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float t[3]; long long own, nbr; bool second;
+  if (!grad_term(a, e, t, own, nbr, second)) return;
+  float* o = (second ? a.g2 : a.g1) + own * 3;
+  o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+}
+
+__global__ void __launch_bounds__(256) grad_scatter_kernel(const GradArgs a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  float t[3] = {0.f, 0.f, 0.f}; long long own, nbr = -1; bool second = false;
+  const bool live = grad_term(a, e, t, own, nbr, second);
+  // the neighbour's slot lives in the OTHER gradient; key = slot with the direction in the top bit
+  const unsigned long long key = live ? ((unsigned long long)nbr | (second ? 1ull << 62 : 0ull)) : ~0ull - lane;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(peers) - 1;
+  float sx = t[0], sy = t[1], sz = t[2];
+  for (unsigned rest = peers & (peers - 1); rest; rest &= rest - 1) {      // same trip count for every lane of the group
+    const int src = __ffs(rest) - 1;
+    const float vx = __shfl_sync(peers, t[0], src), vy = __shfl_sync(peers, t[1], src), vz = __shfl_sync(peers, t[2], src);
+    if (lane == leader) { sx += vx; sy += vy; sz += vz; }
+  }
+  if (live && lane == leader) {
+    float* o = (second ? a.g1 : a.g2) + nbr * 3;
+    atomicAdd(o + 0, -sx); atomicAdd(o + 1, -sy); atomicAdd(o + 2, -sz);
   }
 }
 
@@ -849,17 +885,20 @@ extern "C" int dusty_chamfer_backward(const float* xyz1, const float* xyz2, int 
   if (b < 0 || n < 0 || m < 0) return fail_arg(DUSTY_EINVAL, "chamfer_backward: negative size");
   if (b == 0) return 0;
   if (int rc = check_device()) return rc;
-  if (n) DUSTY_CUDA(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * b * n, st));
-  if (m) DUSTY_CUDA(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * b * m, st));
-  if (n == 0 || m == 0) return 0;
+  if (n == 0 || m == 0) {            // no neighbours: the reference's memsets are all that happens
+    if (n) DUSTY_CUDA(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * b * n, st));
+    if (m) DUSTY_CUDA(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * b * m, st));
+    return 0;
+  }
   if (!xyz1 || !xyz2 || !grad_dist1 || !grad_dist2 || !idx1 || !idx2 || !grad_xyz1 || !grad_xyz2)
     return fail_arg(DUSTY_EINVAL, "chamfer_backward: null pointer");
-  const int g1 = (int)std::min<long long>(((long long)b * n + 255) / 256, 148LL * 16);
-  grad_kernel<<<g1, 256, 0, st>>>(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_xyz1, grad_xyz2);
-  DUSTY_AFTER_LAUNCH("chamfer grad_kernel");
-  const int g2 = (int)std::min<long long>(((long long)b * m + 255) / 256, 148LL * 16);
-  grad_kernel<<<g2, 256, 0, st>>>(b, m, xyz2, n, xyz1, grad_dist2, idx2, grad_xyz2, grad_xyz1);
-  DUSTY_AFTER_LAUNCH("chamfer grad_kernel");
+  const GradArgs a{b, n, m, xyz1, xyz2, grad_dist1, grad_dist2, idx1, idx2, grad_xyz1, grad_xyz2};
+  const long long total = (long long)b * n + (long long)b * m;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  grad_own_kernel<<<grid, 256, 0, st>>>(a);
+  DUSTY_AFTER_LAUNCH("chamfer grad_own_kernel");
+  grad_scatter_kernel<<<grid, 256, 0, st>>>(a);
+  DUSTY_AFTER_LAUNCH("chamfer grad_scatter_kernel");
   return 0;
 }
 

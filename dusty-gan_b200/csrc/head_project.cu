@@ -22,8 +22,7 @@ namespace dusty {
 namespace head {
 
 constexpr int TPB = 256;
-constexpr int GROUP = TPB * 4;          // pixels per CTA and iteration (1024)
-constexpr int MAX_ITERS = 4;
+constexpr int GROUP = TPB * 4;          // pixels per CTA (1024)
 
 struct GateDev {
   int mode;
@@ -46,6 +45,7 @@ struct Args {
   int* out_index;
   float* out_compact;
   unsigned* seg_state;      // one word per CTA: 0x80000000 | count once published
+  unsigned* ticket;         // compaction: segments are handed out in the order the CTAs start running
   int npix;                 // h*w
   int segs_per_image;
 };
@@ -61,7 +61,7 @@ __device__ __forceinline__ float gate_value(float logit, int mode, float na, flo
   if (mode == DUSTY_NOISE_NONE) return logit > 0.0f ? 1.0f : 0.0f;
   const float l = mode == DUSTY_NOISE_UNIFORM ? logistic_from_uniform(na, nb, p.eps) : na;
   const float x = __fmul_rn(__fadd_rn(logit, l), p.inv_tau);
-  const float soft = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+  const float soft = __frcp_rn(__fadd_rn(1.0f, expf(-x)));     // == 1.0f / y: both are the correctly rounded quotient
   const float hard = soft > p.threshold ? 1.0f : 0.0f;
   return __fadd_rn(__fsub_rn(hard, soft), soft);
 }
@@ -77,25 +77,39 @@ __device__ __forceinline__ float4 load_noise(const GateDev& g, const float* base
 __device__ __forceinline__ float range_from_inv(float inv, const dusty_head_params& p, bool& valid) {
   valid = fabsf(inv) > p.tol;
   const float disp = __fadd_rn(__fmul_rn(inv, p.disp_scale), p.disp_shift);
-  const float depth = __fdiv_rn(1.0f, disp);
+  const float depth = __frcp_rn(disp);                         // == 1.0f / disp, correctly rounded
   const float nrm = __fmul_rn(__fsub_rn(depth, p.min_depth), p.inv_range);
   float d = __fadd_rn(__fmul_rn(nrm, p.range), p.min_depth);
   d = __fmul_rn(d, p.inv_max_depth);
   return __fmul_rn(d, valid ? 1.0f : 0.0f);
 }
 
-// ITERS 4-pixel groups per thread: more independent 128-bit loads in flight per thread against
-// finer CTAs, fewer registers and more resident warps; see pick_iters for the measurement.
-template <int C, bool COMPACT, int ITERS>
-__global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
-  constexpr int SEG = GROUP * ITERS;
-  __shared__ int wsum[2][TPB / 32];
+// One 4-pixel group per thread (32 registers -> 8 CTAs = 2048 threads per SM, 1024 pixels per CTA): occupancy
+// hides the latency, the last wave is small (measured against 2 and 4 groups per thread: DESIGN.md 2.1).
+//
+// Ordered compaction (COMPACT): the valid pixels of an image, in pixel order. A CTA packs its own valid points
+// into shared memory (block scan), publishes their number, sums the numbers of the earlier segments of its image
+// (one warp reads them in parallel: a single L2 round trip) and copies its packed block to the image's output
+// with coalesced stores. The segments of an image are handed out by a per-image ticket counter to the CTAs that
+// blockIdx assigns to that image, so every segment a CTA waits for belongs to a CTA that is already running --
+// the hardware does not promise to start CTAs in blockIdx order.
+template <int C, bool COMPACT>
+__global__ void __launch_bounds__(TPB, C == 1 ? 8 : 7) head_project_kernel(const Args a) {
+  constexpr int SEG = GROUP;
+  // per-warp transpose buffers for the interleaved points (8 x 384 floats); with compaction the same memory then
+  // stages the CTA's packed points (3 x 1024 floats) and their pixel indices (1024 ints)
+  __shared__ __align__(16) float stage[COMPACT ? 4 * GROUP : (TPB / 32) * 384];
+  __shared__ int wsum[TPB / 32];
   __shared__ int s_base;
-  __shared__ __align__(16) float xyz_stage[TPB / 32][384];     // per-warp transpose buffer for interleaved points
   const dusty_head_params& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long img = blockIdx.x / a.segs_per_image;
-  const int seg = blockIdx.x - (int)img * a.segs_per_image;
+  int seg = (int)(blockIdx.x - (unsigned)img * a.segs_per_image);
+  if (COMPACT && a.ticket != nullptr) {        // one counter per image, 128 bytes apart: no single hot address
+    if (tid == 0) s_base = (int)atomicAdd(a.ticket + img * 32, 1u);
+    __syncthreads();
+    seg = s_base;
+  }
   const int npix = a.npix;
 
   const float* depth = a.depth + img * npix;
@@ -103,69 +117,53 @@ __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
   float* omask0 = a.out_mask + img * C * npix;
   float* odepth = a.out_depth + img * npix;
 
-  float4 xs[ITERS], ys[ITERS], zs[ITERS];
-  unsigned vbits[ITERS];
-  int tcount = 0;
-
-  // all streaming loads of this thread first: 2-3 independent 128-bit requests per iteration in flight
-  float4 dvs[ITERS], cvs[ITERS], c1s[C == 2 ? ITERS : 1];
-  #pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    const int pix = seg * SEG + it * (TPB * 4) + tid * 4;
-    if (pix < npix) {
-      dvs[it] = ldg_stream(reinterpret_cast<const float4*>(depth + pix));
-      cvs[it] = ldg_stream(reinterpret_cast<const float4*>(conf0 + pix));
-      if (C == 2) c1s[it] = ldg_stream(reinterpret_cast<const float4*>(conf0 + npix + pix));
-    }
-  }
-
-  #pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    const int pix = seg * SEG + it * (TPB * 4) + tid * 4;
-    vbits[it] = 0;
-    if (pix < npix) {
-      const float4 dv = dvs[it];
-      const float4 cv = cvs[it];
-      float4 na = make_float4(0, 0, 0, 0), nb = na;
-      if (a.gp.mode != DUSTY_NOISE_NONE) na = load_noise(a.gp, a.gp.a, img, pix);
-      if (a.gp.mode == DUSTY_NOISE_UNIFORM) nb = load_noise(a.gp, a.gp.b, img, pix);
-      float mp[4] = {gate_value(cv.x, a.gp.mode, na.x, nb.x, p), gate_value(cv.y, a.gp.mode, na.y, nb.y, p),
-                     gate_value(cv.z, a.gp.mode, na.z, nb.z, p), gate_value(cv.w, a.gp.mode, na.w, nb.w, p)};
-      float mk[4] = {mp[0], mp[1], mp[2], mp[3]};
-      stg_stream(reinterpret_cast<float4*>(omask0 + pix), make_float4(mp[0], mp[1], mp[2], mp[3]));
-      if (C == 2) {
-        const float4 c1 = c1s[C == 2 ? it : 0];
-        float4 ia = make_float4(0, 0, 0, 0), ib = ia;
-        if (a.gi.mode != DUSTY_NOISE_NONE) ia = load_noise(a.gi, a.gi.a, img, pix);
-        if (a.gi.mode == DUSTY_NOISE_UNIFORM) ib = load_noise(a.gi, a.gi.b, img, pix);
-        const float mi[4] = {gate_value(c1.x, a.gi.mode, ia.x, ib.x, p), gate_value(c1.y, a.gi.mode, ia.y, ib.y, p),
-                             gate_value(c1.z, a.gi.mode, ia.z, ib.z, p), gate_value(c1.w, a.gi.mode, ia.w, ib.w, p)};
-        stg_stream(reinterpret_cast<float4*>(omask0 + npix + pix), make_float4(mi[0], mi[1], mi[2], mi[3]));
-        #pragma unroll
-        for (int q = 0; q < 4; ++q) mk[q] = __fmul_rn(mp[q], mi[q]);
-      }
-      const float din[4] = {dv.x, dv.y, dv.z, dv.w};
-      float dout[4], rng[4];
+  const int pix = seg * SEG + tid * 4;
+  unsigned vbits = 0;
+  float X[4] = {0.f, 0.f, 0.f, 0.f}, Y[4] = {0.f, 0.f, 0.f, 0.f}, Z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pix < npix) {
+    // the streaming loads of this thread first: 2-3 independent 128-bit requests in flight
+    const float4 dv = ldg_stream(reinterpret_cast<const float4*>(depth + pix));
+    const float4 cv = ldg_stream(reinterpret_cast<const float4*>(conf0 + pix));
+    float4 c1 = make_float4(0, 0, 0, 0);
+    if (C == 2) c1 = ldg_stream(reinterpret_cast<const float4*>(conf0 + npix + pix));
+    float4 na = make_float4(0, 0, 0, 0), nb = na;
+    if (a.gp.mode != DUSTY_NOISE_NONE) na = load_noise(a.gp, a.gp.a, img, pix);
+    if (a.gp.mode == DUSTY_NOISE_UNIFORM) nb = load_noise(a.gp, a.gp.b, img, pix);
+    float mp[4] = {gate_value(cv.x, a.gp.mode, na.x, nb.x, p), gate_value(cv.y, a.gp.mode, na.y, nb.y, p),
+                   gate_value(cv.z, a.gp.mode, na.z, nb.z, p), gate_value(cv.w, a.gp.mode, na.w, nb.w, p)};
+    float mk[4] = {mp[0], mp[1], mp[2], mp[3]};
+    stg_stream(reinterpret_cast<float4*>(omask0 + pix), make_float4(mp[0], mp[1], mp[2], mp[3]));
+    if (C == 2) {
+      float4 ia = make_float4(0, 0, 0, 0), ib = ia;
+      if (a.gi.mode != DUSTY_NOISE_NONE) ia = load_noise(a.gi, a.gi.a, img, pix);
+      if (a.gi.mode == DUSTY_NOISE_UNIFORM) ib = load_noise(a.gi, a.gi.b, img, pix);
+      const float mi[4] = {gate_value(c1.x, a.gi.mode, ia.x, ib.x, p), gate_value(c1.y, a.gi.mode, ia.y, ib.y, p),
+                           gate_value(c1.z, a.gi.mode, ia.z, ib.z, p), gate_value(c1.w, a.gi.mode, ia.w, ib.w, p)};
+      stg_stream(reinterpret_cast<float4*>(omask0 + npix + pix), make_float4(mi[0], mi[1], mi[2], mi[3]));
       #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        // mask * depth + (1 - mask) * drop_const
-        dout[q] = __fadd_rn(__fmul_rn(mk[q], din[q]), __fmul_rn(__fsub_rn(1.0f, mk[q]), p.drop_const));
-        // tanh_to_sigmoid + clamp_(0,1); NaN survives the clamp as in torch
-        float inv = __fmul_rn(__fadd_rn(dout[q], 1.0f), 0.5f);
-        inv = inv < 0.0f ? 0.0f : (inv > 1.0f ? 1.0f : inv);
-        bool valid;
-        rng[q] = range_from_inv(inv, p, valid);
-        vbits[it] |= valid ? (1u << q) : 0u;
-      }
-      stg_stream(reinterpret_cast<float4*>(odepth + pix), make_float4(dout[0], dout[1], dout[2], dout[3]));
-      if (!COMPACT && a.out_points == nullptr) continue;   // maskout alone: no projection, no trig table
+      for (int q = 0; q < 4; ++q) mk[q] = __fmul_rn(mp[q], mi[q]);
+    }
+    const float din[4] = {dv.x, dv.y, dv.z, dv.w};
+    float dout[4], rng[4];
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // mask * depth + (1 - mask) * drop_const
+      dout[q] = __fadd_rn(__fmul_rn(mk[q], din[q]), __fmul_rn(__fsub_rn(1.0f, mk[q]), p.drop_const));
+      // tanh_to_sigmoid + clamp_(0,1); NaN survives the clamp as in torch
+      float inv = __fmul_rn(__fadd_rn(dout[q], 1.0f), 0.5f);
+      inv = inv < 0.0f ? 0.0f : (inv > 1.0f ? 1.0f : inv);
+      bool valid;
+      rng[q] = range_from_inv(inv, p, valid);
+      vbits |= valid ? (1u << q) : 0u;
+    }
+    stg_stream(reinterpret_cast<float4*>(odepth + pix), make_float4(dout[0], dout[1], dout[2], dout[3]));
+    if (COMPACT || a.out_points != nullptr) {                 // maskout alone: no projection, no trig table
       const float4 ce = *reinterpret_cast<const float4*>(a.trig + pix);
       const float4 se = *reinterpret_cast<const float4*>(a.trig + npix + pix);
       const float4 ca = *reinterpret_cast<const float4*>(a.trig + 2 * npix + pix);
       const float4 sa = *reinterpret_cast<const float4*>(a.trig + 3 * npix + pix);
       const float cev[4] = {ce.x, ce.y, ce.z, ce.w}, sev[4] = {se.x, se.y, se.z, se.w};
       const float cav[4] = {ca.x, ca.y, ca.z, ca.w}, sav[4] = {sa.x, sa.y, sa.z, sa.w};
-      float X[4], Y[4], Z[4];
       #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float rc = __fmul_rn(rng[q], cev[q]);
@@ -173,30 +171,26 @@ __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
         Y[q] = __fmul_rn(rc, sav[q]);
         Z[q] = __fmul_rn(rng[q], sev[q]);
       }
-      xs[it] = make_float4(X[0], X[1], X[2], X[3]);
-      ys[it] = make_float4(Y[0], Y[1], Y[2], Y[3]);
-      zs[it] = make_float4(Z[0], Z[1], Z[2], Z[3]);
       if (a.out_points != nullptr) {
         if (p.points_layout == 0) {
           float* o = a.out_points + img * 3 * npix + pix;
-          stg_stream(reinterpret_cast<float4*>(o), xs[it]);
-          stg_stream(reinterpret_cast<float4*>(o + npix), ys[it]);
-          stg_stream(reinterpret_cast<float4*>(o + 2 * npix), zs[it]);
+          stg_stream(reinterpret_cast<float4*>(o), make_float4(X[0], X[1], X[2], X[3]));
+          stg_stream(reinterpret_cast<float4*>(o + npix), make_float4(Y[0], Y[1], Y[2], Y[3]));
+          stg_stream(reinterpret_cast<float4*>(o + 2 * npix), make_float4(Z[0], Z[1], Z[2], Z[3]));
         } else {
-          const int wpix = seg * SEG + it * (TPB * 4) + warp * 128;       // first pixel of this warp's 128
+          const int wpix = seg * SEG + warp * 128;       // first pixel of this warp's 128
           if (wpix + 128 <= npix) {
             // whole warp in range (uniform): transpose through shared memory so that every STG.128 of
             // the warp covers 512 contiguous bytes instead of 16 bytes out of every 48
-            float4* stage = reinterpret_cast<float4*>(xyz_stage[warp]);
-            stage[lane * 3] = make_float4(X[0], Y[0], Z[0], X[1]);
-            stage[lane * 3 + 1] = make_float4(Y[1], Z[1], X[2], Y[2]);
-            stage[lane * 3 + 2] = make_float4(Z[2], X[3], Y[3], Z[3]);
+            float4* wst = reinterpret_cast<float4*>(stage + warp * 384);
+            wst[lane * 3] = make_float4(X[0], Y[0], Z[0], X[1]);
+            wst[lane * 3 + 1] = make_float4(Y[1], Z[1], X[2], Y[2]);
+            wst[lane * 3 + 2] = make_float4(Z[2], X[3], Y[3], Z[3]);
             __syncwarp();
             float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + wpix) * 3);
-            stg_stream(o + lane, stage[lane]);
-            stg_stream(o + lane + 32, stage[lane + 32]);
-            stg_stream(o + lane + 64, stage[lane + 64]);
-            __syncwarp();
+            stg_stream(o + lane, wst[lane]);
+            stg_stream(o + lane + 32, wst[lane + 32]);
+            stg_stream(o + lane + 64, wst[lane + 64]);
           } else {
             float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + pix) * 3);
             stg_stream(o, make_float4(X[0], Y[0], Z[0], X[1]));
@@ -205,66 +199,208 @@ __global__ void __launch_bounds__(TPB) head_project_kernel(const Args a) {
           }
         }
       }
-      tcount += __popc(vbits[it]);
     }
   }
-
   if (!COMPACT) return;
 
-  // ---- ordered compaction: positions follow pixel order within the image ----
-  // 1. CTA total -> publish; 2. look back over the earlier segments of this image; 3. scatter.
-  int total = tcount;
+  // ---- ordered compaction ----
+  const int c = __popc(vbits);
+  int inc = c;
   #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  if (lane == 0) wsum[0][warp] = total;
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  __syncthreads();                       // every warp is done with its transpose buffer (and with s_base)
+  if (lane == 31) wsum[warp] = inc;
   __syncthreads();
-  if (tid == 0) {
-    int cta_total = 0;
-    #pragma unroll
-    for (int w = 0; w < TPB / 32; ++w) cta_total += wsum[0][w];
-    volatile unsigned* st = a.seg_state + img * a.segs_per_image;
-    st[seg] = 0x80000000u | (unsigned)cta_total;
-    __threadfence();
-    int base = 0;
-    for (int s = 0; s < seg; ++s) {
-      unsigned v;
-      do { v = st[s]; } while (!(v & 0x80000000u));
-      base += (int)(v & 0x7fffffffu);
+  int before = 0, cta_total = 0;
+  #pragma unroll
+  for (int w = 0; w < TPB / 32; ++w) { const int sw = wsum[w]; if (w < warp) before += sw; cta_total += sw; }
+  volatile unsigned* st = a.seg_state + img * a.segs_per_image;
+  if (tid == 0) st[seg] = 0x80000000u | (unsigned)cta_total;      // the word carries the count itself: nothing to fence
+  float* const cxyz = stage;
+  int* const cidx = reinterpret_cast<int*>(stage + 3 * GROUP);
+  int pos = before + inc - c;
+  #pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (vbits & (1u << q)) {
+      cxyz[3 * pos] = X[q]; cxyz[3 * pos + 1] = Y[q]; cxyz[3 * pos + 2] = Z[q];
+      cidx[pos] = pix + q;
+      ++pos;
     }
-    s_base = base;
-    if (seg == a.segs_per_image - 1 && a.out_count) a.out_count[img] = base + cta_total;
+  }
+  if (warp == 0) {                       // earlier segments of this image, 32 at a time, in parallel
+    int base = 0;
+    for (int s0 = 0; s0 < seg; s0 += 32) {
+      unsigned v = 0x80000000u;
+      if (s0 + lane < seg) { do { v = st[s0 + lane]; } while (!(v & 0x80000000u)); }
+      base += (int)__reduce_add_sync(0xffffffffu, v & 0x7fffffffu);
+    }
+    if (lane == 0) {
+      s_base = base;
+      if (seg == a.segs_per_image - 1 && a.out_count) a.out_count[img] = base + cta_total;
+    }
   }
   __syncthreads();
-  int running = s_base;
-  #pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    const int c = __popc(vbits[it]);
+  const long long first = img * npix + s_base;
+  if (a.out_compact) {
+    float* o = a.out_compact + first * 3;
+    for (int i = tid; i < 3 * cta_total; i += TPB) o[i] = cxyz[i];
+  }
+  if (a.out_index) {
+    int* o = a.out_index + first;
+    for (int i = tid; i < cta_total; i += TPB) o[i] = cidx[i];
+  }
+}
+
+// Compaction for large batches: one CTA of 512 threads owns a whole image and walks it in 2048-pixel steps with the
+// next step's loads already in flight, so the running number of valid pixels never leaves the CTA: no look-back,
+// no tickets, no waiting on other CTAs (the segment kernel above spends its time exactly there: each CTA is a
+// chain of ticket -> loads -> count -> look-back -> copy, and only a few CTAs fit an SM). Every warp packs its
+// valid points through its own shared-memory buffer and writes them with coalesced stores. Used when the batch
+// alone fills the GPU (b >= 128 images); the arithmetic is the same code as above, bit for bit.
+constexpr int IMG_TPB = 512;
+
+template <int C>
+__global__ void __launch_bounds__(IMG_TPB, 2) head_project_image_kernel(const Args a) {
+  constexpr int NWARP = IMG_TPB / 32;
+  __shared__ __align__(16) float stage[NWARP * 384];      // per-warp: transpose of 128 points, then its packed points
+  __shared__ int istage[NWARP * 128];                     // per-warp: pixel indices of its packed points
+  __shared__ int wsum[2][NWARP];
+  const dusty_head_params& p = a.p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long img = blockIdx.x;
+  const int npix = a.npix;
+  const float* depth = a.depth + img * npix;
+  const float* conf0 = a.conf + img * C * npix;
+  float* omask0 = a.out_mask + img * C * npix;
+  float* odepth = a.out_depth + img * npix;
+  float* const wst = stage + warp * 384;
+  int* const wix = istage + warp * 128;
+  const int steps = (npix + IMG_TPB * 4 - 1) / (IMG_TPB * 4);
+
+  float4 dv = make_float4(0, 0, 0, 0), cv = dv, c1 = dv;
+  if (tid * 4 < npix) {
+    dv = ldg_stream(reinterpret_cast<const float4*>(depth + tid * 4));
+    cv = ldg_stream(reinterpret_cast<const float4*>(conf0 + tid * 4));
+    if (C == 2) c1 = ldg_stream(reinterpret_cast<const float4*>(conf0 + npix + tid * 4));
+  }
+  int running = 0;
+  for (int it = 0; it < steps; ++it) {
+    const int pix = it * (IMG_TPB * 4) + tid * 4;
+    const float4 dcur = dv, ccur = cv, c1cur = c1;
+    const int nxt = pix + IMG_TPB * 4;
+    if (it + 1 < steps && nxt < npix) {                   // next step's streaming loads
+      dv = ldg_stream(reinterpret_cast<const float4*>(depth + nxt));
+      cv = ldg_stream(reinterpret_cast<const float4*>(conf0 + nxt));
+      if (C == 2) c1 = ldg_stream(reinterpret_cast<const float4*>(conf0 + npix + nxt));
+    }
+    unsigned vbits = 0;
+    float X[4] = {0.f, 0.f, 0.f, 0.f}, Y[4] = {0.f, 0.f, 0.f, 0.f}, Z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pix < npix) {
+      float4 na = make_float4(0, 0, 0, 0), nb = na;
+      if (a.gp.mode != DUSTY_NOISE_NONE) na = load_noise(a.gp, a.gp.a, img, pix);
+      if (a.gp.mode == DUSTY_NOISE_UNIFORM) nb = load_noise(a.gp, a.gp.b, img, pix);
+      float mp[4] = {gate_value(ccur.x, a.gp.mode, na.x, nb.x, p), gate_value(ccur.y, a.gp.mode, na.y, nb.y, p),
+                     gate_value(ccur.z, a.gp.mode, na.z, nb.z, p), gate_value(ccur.w, a.gp.mode, na.w, nb.w, p)};
+      float mk[4] = {mp[0], mp[1], mp[2], mp[3]};
+      stg_stream(reinterpret_cast<float4*>(omask0 + pix), make_float4(mp[0], mp[1], mp[2], mp[3]));
+      if (C == 2) {
+        float4 ia = make_float4(0, 0, 0, 0), ib = ia;
+        if (a.gi.mode != DUSTY_NOISE_NONE) ia = load_noise(a.gi, a.gi.a, img, pix);
+        if (a.gi.mode == DUSTY_NOISE_UNIFORM) ib = load_noise(a.gi, a.gi.b, img, pix);
+        const float mi[4] = {gate_value(c1cur.x, a.gi.mode, ia.x, ib.x, p), gate_value(c1cur.y, a.gi.mode, ia.y, ib.y, p),
+                             gate_value(c1cur.z, a.gi.mode, ia.z, ib.z, p), gate_value(c1cur.w, a.gi.mode, ia.w, ib.w, p)};
+        stg_stream(reinterpret_cast<float4*>(omask0 + npix + pix), make_float4(mi[0], mi[1], mi[2], mi[3]));
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) mk[q] = __fmul_rn(mp[q], mi[q]);
+      }
+      const float din[4] = {dcur.x, dcur.y, dcur.z, dcur.w};
+      float dout[4], rng[4];
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dout[q] = __fadd_rn(__fmul_rn(mk[q], din[q]), __fmul_rn(__fsub_rn(1.0f, mk[q]), p.drop_const));
+        float inv = __fmul_rn(__fadd_rn(dout[q], 1.0f), 0.5f);
+        inv = inv < 0.0f ? 0.0f : (inv > 1.0f ? 1.0f : inv);
+        bool valid;
+        rng[q] = range_from_inv(inv, p, valid);
+        vbits |= valid ? (1u << q) : 0u;
+      }
+      stg_stream(reinterpret_cast<float4*>(odepth + pix), make_float4(dout[0], dout[1], dout[2], dout[3]));
+      const float4 ce = *reinterpret_cast<const float4*>(a.trig + pix);
+      const float4 se = *reinterpret_cast<const float4*>(a.trig + npix + pix);
+      const float4 ca = *reinterpret_cast<const float4*>(a.trig + 2 * npix + pix);
+      const float4 sa = *reinterpret_cast<const float4*>(a.trig + 3 * npix + pix);
+      const float cev[4] = {ce.x, ce.y, ce.z, ce.w}, sev[4] = {se.x, se.y, se.z, se.w};
+      const float cav[4] = {ca.x, ca.y, ca.z, ca.w}, sav[4] = {sa.x, sa.y, sa.z, sa.w};
+      #pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float rc = __fmul_rn(rng[q], cev[q]);
+        X[q] = __fmul_rn(rc, cav[q]);
+        Y[q] = __fmul_rn(rc, sav[q]);
+        Z[q] = __fmul_rn(rng[q], sev[q]);
+      }
+    }
+    const int wpix = it * (IMG_TPB * 4) + warp * 128;     // first pixel of this warp's 128
+    if (a.out_points != nullptr) {
+      if (p.points_layout == 0) {
+        if (pix < npix) {
+          float* o = a.out_points + img * 3 * npix + pix;
+          stg_stream(reinterpret_cast<float4*>(o), make_float4(X[0], X[1], X[2], X[3]));
+          stg_stream(reinterpret_cast<float4*>(o + npix), make_float4(Y[0], Y[1], Y[2], Y[3]));
+          stg_stream(reinterpret_cast<float4*>(o + 2 * npix), make_float4(Z[0], Z[1], Z[2], Z[3]));
+        }
+      } else if (wpix + 128 <= npix) {                    // warp-uniform
+        float4* w4 = reinterpret_cast<float4*>(wst);
+        w4[lane * 3] = make_float4(X[0], Y[0], Z[0], X[1]);
+        w4[lane * 3 + 1] = make_float4(Y[1], Z[1], X[2], Y[2]);
+        w4[lane * 3 + 2] = make_float4(Z[2], X[3], Y[3], Z[3]);
+        __syncwarp();
+        float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + wpix) * 3);
+        stg_stream(o + lane, w4[lane]);
+        stg_stream(o + lane + 32, w4[lane + 32]);
+        stg_stream(o + lane + 64, w4[lane + 64]);
+        __syncwarp();
+      } else if (pix < npix) {
+        float4* o = reinterpret_cast<float4*>(a.out_points + (img * npix + pix) * 3);
+        stg_stream(o, make_float4(X[0], Y[0], Z[0], X[1]));
+        stg_stream(o + 1, make_float4(Y[1], Z[1], X[2], Y[2]));
+        stg_stream(o + 2, make_float4(Z[2], X[3], Y[3], Z[3]));
+      }
+    }
+    // ---- ordered compaction: warp scan, one barrier per step (double-buffered warp sums), packed warp stores ----
+    const int c = __popc(vbits);
     int inc = c;
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const int wcount = __shfl_sync(0xffffffffu, inc, 31);
     if (lane == 31) wsum[it & 1][warp] = inc;
-    __syncthreads();
-    int before = 0, all = 0;
-    #pragma unroll
-    for (int w = 0; w < TPB / 32; ++w) { const int s = wsum[it & 1][w]; if (w < warp) before += s; all += s; }
-    int pos = running + before + inc - c;
-    running += all;
-    const int pix = seg * SEG + it * (TPB * 4) + tid * 4;
-    const float X[4] = {xs[it].x, xs[it].y, xs[it].z, xs[it].w};
-    const float Y[4] = {ys[it].x, ys[it].y, ys[it].z, ys[it].w};
-    const float Z[4] = {zs[it].x, zs[it].y, zs[it].z, zs[it].w};
+    int off = inc - c;
     #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (vbits[it] & (1u << q)) {
-        if (a.out_index) a.out_index[img * npix + pos] = pix + q;
-        if (a.out_compact) {
-          float* o = a.out_compact + (img * npix + pos) * 3;
-          o[0] = X[q]; o[1] = Y[q]; o[2] = Z[q];
-        }
-        ++pos;
+      if (vbits & (1u << q)) {
+        wst[3 * off] = X[q]; wst[3 * off + 1] = Y[q]; wst[3 * off + 2] = Z[q];
+        wix[off] = pix + q;
+        ++off;
       }
     }
+    __syncthreads();
+    int ws = lane < NWARP ? wsum[it & 1][lane] : 0;       // inclusive scan of the 16 warp sums by shuffles
+    #pragma unroll
+    for (int o = 1; o < NWARP; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+    const int total = __shfl_sync(0xffffffffu, ws, NWARP - 1);
+    const int before = warp == 0 ? 0 : __shfl_sync(0xffffffffu, ws, warp - 1);
+    const long long first = img * npix + running + before;
+    if (a.out_compact) {
+      float* o = a.out_compact + first * 3;
+      for (int i = lane; i < 3 * wcount; i += 32) o[i] = wst[i];
+    }
+    if (a.out_index) {
+      int* o = a.out_index + first;
+      for (int i = lane; i < wcount; i += 32) o[i] = wix[i];
+    }
+    __syncwarp();
+    running += total;
   }
+  if (tid == 0 && a.out_count) a.out_count[img] = running;
 }
 
 __global__ void __launch_bounds__(TPB) inv_to_xyz_kernel(const dusty_head_params p, const float* __restrict__ inv_all,
@@ -323,16 +459,6 @@ __global__ void __launch_bounds__(TPB) gumbel_sigmoid_kernel(const float* __rest
                          gate_value(cv.z, g.mode, na.z, nb.z, p), gate_value(cv.w, g.mode, na.w, nb.w, p)));
 }
 
-// Pixel groups per thread. Measured on B200 (tests/perf_head_iters.py, batch 256 of 64x512, DUSty-I):
-// ITERS = 4 (62 registers, 4 CTAs/SM, 2048 CTAs = 3.46 waves) 43.3 us; ITERS = 2 (42 registers) 39.1 us;
-// ITERS = 1 (32 registers, 8 CTAs/SM = 2048 threads/SM, 8192 CTAs) 37.4 us = 6.29 TB/s. One group per
-// thread wins at every batch size: full occupancy hides the latency that the extra loads per thread
-// were meant to hide, and the last wave is small. DUSTY_HEAD_ITERS=2|4 re-creates the A/B.
-static int pick_iters(int, int) {
-  if (const char* e = getenv("DUSTY_HEAD_ITERS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) return v; }
-  return 1;
-}
-
 static int check_params(const dusty_head_params* p, const char* who) {
   if (!p) return fail_arg(DUSTY_EINVAL, "%s: null params", who);
   if (p->b < 0 || p->h <= 0 || p->w <= 0) return fail_arg(DUSTY_EINVAL, "%s: bad shape b=%d h=%d w=%d", who, p->b, p->h, p->w);
@@ -364,7 +490,7 @@ extern "C" size_t dusty_head_project_workspace_bytes(int b, int h, int w) {
   if (b <= 0 || h <= 0 || w <= 0) return 0;
   const long long npix = (long long)h * w;
   const long long segs = (npix + GROUP - 1) / GROUP;      // the finest segmentation any launch uses
-  return align_up((size_t)b * segs * sizeof(unsigned), 256);
+  return align_up(((size_t)b * segs + (size_t)b * 32) * sizeof(unsigned), 256);      // segment states + per-image ticket counters
 }
 
 extern "C" int dusty_head_project(const dusty_head_params* p, const float* depth, const float* confidence,
@@ -393,29 +519,34 @@ extern "C" int dusty_head_project(const dusty_head_params* p, const float* depth
   a.out_mask = out_mask; a.out_depth = out_depth; a.out_points = out_points;
   a.out_count = out_count; a.out_index = out_index; a.out_compact = out_compact;
   a.npix = p->h * p->w;
-  const int iters = pick_iters(p->b, a.npix);
-  const int seg = GROUP * iters;
-  a.segs_per_image = (a.npix + seg - 1) / seg;
+  a.segs_per_image = (a.npix + GROUP - 1) / GROUP;
   const long long ctas = (long long)p->b * a.segs_per_image;
   if (ctas > 0x7fffffffLL) return fail_arg(DUSTY_EINVAL, "head_project: grid too large");
   if (compact) {
     if (!workspace || workspace_bytes < dusty_head_project_workspace_bytes(p->b, p->h, p->w))
       return fail_arg(DUSTY_ENOSPACE, "head_project: compaction needs %zu workspace bytes", dusty_head_project_workspace_bytes(p->b, p->h, p->w));
     a.seg_state = static_cast<unsigned*>(workspace);
-    DUSTY_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ctas * sizeof(unsigned), st));
+    a.ticket = a.seg_state + ctas;
+    static const bool no_ticket = [] { const char* e = getenv("DUSTY_HEAD_TICKET"); return e && e[0] == '0'; }();   // A/B only
+    DUSTY_CUDA(cudaMemsetAsync(workspace, 0, ((size_t)ctas + (size_t)p->b * 32) * sizeof(unsigned), st));
+    if (no_ticket) a.ticket = nullptr;
   }
-#define DUSTY_HEAD_LAUNCH(C, COMPACT)                                                                     \
-  switch (iters) {                                                                                        \
-    case 1: head_project_kernel<C, COMPACT, 1><<<(unsigned)ctas, TPB, 0, st>>>(a); break;                 \
-    case 2: head_project_kernel<C, COMPACT, 2><<<(unsigned)ctas, TPB, 0, st>>>(a); break;                 \
-    default: head_project_kernel<C, COMPACT, 4><<<(unsigned)ctas, TPB, 0, st>>>(a); break;                \
+  // batches that fill the GPU with one CTA per image: no cross-CTA scan at all (DUSTY_HEAD_COMPACT=segment|image forces one)
+  const char* const forced = getenv("DUSTY_HEAD_COMPACT");
+  const int force_path = !forced ? 0 : (forced[0] == 's' ? 1 : (forced[0] == 'i' ? 2 : 0));
+  if (compact && (force_path == 2 || (force_path == 0 && p->b >= 128))) {
+    if (p->conf_channels == 1) head_project_image_kernel<1><<<(unsigned)p->b, IMG_TPB, 0, st>>>(a);
+    else head_project_image_kernel<2><<<(unsigned)p->b, IMG_TPB, 0, st>>>(a);
+    DUSTY_AFTER_LAUNCH("head_project_image_kernel");
+    return 0;
   }
   if (p->conf_channels == 1) {
-    if (compact) { DUSTY_HEAD_LAUNCH(1, true) } else { DUSTY_HEAD_LAUNCH(1, false) }
+    if (compact) head_project_kernel<1, true><<<(unsigned)ctas, TPB, 0, st>>>(a);
+    else head_project_kernel<1, false><<<(unsigned)ctas, TPB, 0, st>>>(a);
   } else {
-    if (compact) { DUSTY_HEAD_LAUNCH(2, true) } else { DUSTY_HEAD_LAUNCH(2, false) }
+    if (compact) head_project_kernel<2, true><<<(unsigned)ctas, TPB, 0, st>>>(a);
+    else head_project_kernel<2, false><<<(unsigned)ctas, TPB, 0, st>>>(a);
   }
-#undef DUSTY_HEAD_LAUNCH
   DUSTY_AFTER_LAUNCH("head_project_kernel");
   return 0;
 }

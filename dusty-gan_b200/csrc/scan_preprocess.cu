@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TPB, 6) scan_preprocess_kernel(const Args a) {
       Z[q] = m ? __fdiv_rn(sz[q], p.max_depth) : 0.0f;
       // invert_depth: denormalize_minmax -> 1/depth -> normalize_minmax over [1/max, 1/min]
       const float depth = __fadd_rn(__fmul_rn(dn[q], p.range), p.min_depth);
-      const float disp = __fdiv_rn(1.0f, depth);
+      const float disp = __frcp_rn(depth);          // == 1.0f / depth, correctly rounded
       const float nd = __fmul_rn(__fsub_rn(disp, p.disp_lo), p.inv_disp_range);
       const float t = __fsub_rn(__fmul_rn(nd, 2.0f), 1.0f);                       // sigmoid_to_tanh
       inv[q] = __fadd_rn(__fmul_rn(mk[q], t), __fmul_rn(__fsub_rn(1.0f, mk[q]), p.drop_const));

@@ -175,8 +175,9 @@ def _drop_value(module):
 
 def _head_call(module, output, threshold, lidar=None, tol=1e-8, points_layout=1, compact=False, buffers=None):
     """Shared body of maskout (lidar=None) and the fused generate->points path (lidar given).
-    ``buffers`` may hold preallocated ``mask``, ``depth``, ``points`` tensors to write into (steady-state
-    callers reuse them; the evaluate loop of the reference reallocates every batch)."""
+    ``buffers`` may hold preallocated ``mask``, ``depth``, ``points`` (and, for ``compact``, ``valid_count``,
+    ``valid_index``, ``valid_points``, ``workspace``) tensors to write into (steady-state callers reuse them; the
+    evaluate loop of the reference reallocates every batch)."""
     buffers = buffers or {}
     assert isinstance(output, dict)
     assert "confidence" in output
@@ -230,12 +231,21 @@ def _head_call(module, output, threshold, lidar=None, tol=1e-8, points_layout=1,
         if tuple(points.shape) != pshape or points.dtype != torch.float32 or not points.is_contiguous():
             raise ValueError("preallocated points buffer does not match the expected shape/dtype")
         if compact:
-            count = torch.empty(B, device=d.device, dtype=torch.int32)
-            index = torch.empty(B, H * W, device=d.device, dtype=torch.int32)
-            compacted = torch.empty(B, H * W, 3, device=d.device, dtype=torch.float32)
+            def scratch(name, shape, dtype):
+                t = buffers.get(name)
+                if t is None:
+                    return torch.empty(shape, device=d.device, dtype=dtype)
+                if tuple(t.shape) != shape or t.dtype != dtype or t.device != d.device or not t.is_contiguous():
+                    raise ValueError(f"preallocated {name} buffer does not match {shape} {dtype}")
+                return t
+            count = scratch("valid_count", (B,), torch.int32)
+            index = scratch("valid_index", (B, H * W), torch.int32)
+            compacted = scratch("valid_points", (B, H * W, 3), torch.float32)
     lib = _lib.load()
     ws_bytes = lib.dusty_head_project_workspace_bytes(B, H, W) if compact else 0
-    ws = _lib.workspace(ws_bytes, d.device) if compact else None
+    ws = (buffers.get("workspace") if buffers.get("workspace") is not None else _lib.workspace(ws_bytes, d.device)) if compact else None
+    if ws is not None and ws.numel() < ws_bytes:
+        raise ValueError("preallocated workspace is too small")
     with torch.cuda.device(d.device):
         _lib.check(lib.dusty_head_project(C.byref(p), _lib.ptr(d), _lib.ptr(c), _lib.ptr(trig), _lib.ptr(mask),
                                           _lib.ptr(dout), _lib.ptr(points), _lib.ptr(count), _lib.ptr(index),

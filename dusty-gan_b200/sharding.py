@@ -61,12 +61,25 @@ def assemble_symmetric(blocks, n):
     return out
 
 
+def _all_gather_flat(t, group):
+    """all_gather_into_tensor of a contiguous tensor. NCCL gathers device buffers directly over NVLink; gloo
+    (CPU tests, and ranks that share one GPU on a single-GPU box) has no device all-gather, so device tensors
+    are staged through the host there."""
+    _, G = world(group)
+    out = torch.empty(G * t.numel(), device=t.device, dtype=t.dtype)
+    if t.is_cuda and dist.get_backend(group) == "gloo":
+        host = torch.empty(G * t.numel(), dtype=t.dtype)
+        dist.all_gather_into_tensor(host, t.reshape(-1).cpu(), group=group)
+        out.copy_(host)
+    else:
+        dist.all_gather_into_tensor(out, t.reshape(-1), group=group)
+    return out
+
+
 def all_gather_blocks(mine, group=None):
     """The single collective of the matrix path: (cap, n) per rank -> (G, cap, n) on every rank."""
     _, G = world(group)
-    flat = torch.empty(G * mine.shape[0], mine.shape[1], device=mine.device, dtype=mine.dtype)
-    dist.all_gather_into_tensor(flat, mine.contiguous(), group=group)
-    return flat.view(G, mine.shape[0], mine.shape[1])
+    return _all_gather_flat(mine.contiguous(), group).view(G, mine.shape[0], mine.shape[1])
 
 
 def all_gather_keys(keys, group=None):
@@ -74,9 +87,7 @@ def all_gather_keys(keys, group=None):
     _, G = world(group)
     if G == 1:
         return keys.view(1, -1)
-    out = torch.empty(G * keys.numel(), device=keys.device, dtype=keys.dtype)
-    dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
-    return out.view(G, keys.numel())
+    return _all_gather_flat(keys.contiguous(), group).view(G, keys.numel())
 
 
 def symmetric_chamfer_matrix(clouds, group=None):

@@ -89,8 +89,10 @@ DUSTY_API int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Gradient of sum(grad_dist1*dist1)+sum(grad_dist2*dist2) w.r.t. both clouds, given the forward
- * arg-mins. grad_xyz1 (b,n,3) and grad_xyz2 (b,m,3) are overwritten (zeroed, then accumulated with
- * atomicAdd like the reference kernel, so the summation order of colliding targets is not fixed). */
+ * arg-mins. grad_xyz1 (b,n,3) and grad_xyz2 (b,m,3) are overwritten: every element is first written with
+ * its own term 2 g (p - q) (no memset, no atomic), then the neighbour terms of both directions are added
+ * with atomicAdd (warp-aggregated per target), so -- as in the reference kernel -- the summation order of
+ * colliding targets is not fixed. */
 DUSTY_API size_t dusty_chamfer_backward_workspace_bytes(int b, int n, int m);
 DUSTY_API int dusty_chamfer_backward(const float* xyz1, const float* xyz2, int b, int n, int m,
                            const float* grad_dist1, const float* grad_dist2,

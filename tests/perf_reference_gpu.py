@@ -17,7 +17,7 @@ import bench  # noqa: E402
 from oracle import refload  # noqa: E402
 
 
-def timed(fn, iters=3, warmup=1):
+def timed(fn, iters=5, warmup=2):
     return statistics.median(bench.time_events(fn, iters, warmup)) * 1e-3
 
 
@@ -87,6 +87,11 @@ def main():
             q1, q2 = chamfer_distance(ar, br)
             loss = q1.sum() + q2.sum()
         out[f"batch{tag}_ours_bwd_pairs_per_s"] = B / timed(lambda: torch.autograd.grad(loss, (ar, br), retain_graph=True))
+        # like for like with ref_bwd: the C-ABI call alone (the line above also pays autograd's graph walk)
+        from dusty_gan_b200.utils.metrics.distance.cd.chamfer_distance import _scatter_grads
+        out[f"batch{tag}_ours_bwd_abi_pairs_per_s"] = B / timed(lambda: _scatter_grads(a, b, g, g, i1, i2))
+        r1, r2 = ref_bwd(); m1, m2 = _scatter_grads(a, b, g, g, i1, i2)
+        out[f"batch{tag}_bwd_max_abs_diff"] = float(max((r1 - m1).abs().max(), (r2 - m2).abs().max()))
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "ref_gpu.json"), "w") as fh:

@@ -142,7 +142,8 @@ def test_hot_kernels_keep_their_occupancy_shape():
     for frag in ("nn_kernelILi8ELb1ELb0ELi128", "nn_kernelILi8ELb1ELb0ELi64", "nn_kernelILi8ELb1ELb0ELi32", "nn_kernelILi4ELb1ELb1ELi256"):
         n = one(frag)
         assert int(usage[n]) <= 128 and int(local[n]) == 0, frag
-    assert int(usage[one("head_project_kernelILi1ELb0ELi1")]) <= 32
-    assert int(usage[one("head_project_kernelILi2ELb0ELi1")]) <= 40      # DUSty-II: 36 registers, 7 CTAs per SM
+    assert int(usage[one("head_project_kernelILi1ELb0E")]) <= 32         # 8 CTAs of 256 threads per SM
+    assert int(usage[one("head_project_kernelILi2ELb0E")]) <= 36         # DUSty-II: 7 CTAs per SM
+    assert int(usage[one("head_project_kernelILi1ELb1E")]) <= 48         # with compaction: 5 CTAs per SM, 16 KB smem each
     assert int(usage[one("fps_multi_kernel")]) <= 40
     assert int(usage[one("scan_preprocess_kernel")]) <= 40

@@ -26,10 +26,16 @@ def assert_bit_equal(a, b, what):
 
 
 @pytest.mark.parametrize("kind", [1, 2])
-@pytest.mark.parametrize("shape", [(5, 64, 512), (3, 16, 64), (2, 8, 20)])
-def test_fixed_noise_bit_exact_on_device(kind, shape):
+@pytest.mark.parametrize("shape,compaction", [((5, 64, 512), "segment"), ((3, 16, 64), "segment"), ((2, 8, 20), "segment"),
+                                              ((5, 64, 512), "image"), ((2, 8, 20), "image"), ((3, 40, 100), "image"),
+                                              ((130, 64, 512), None)])
+def test_fixed_noise_bit_exact_on_device(kind, shape, compaction, monkeypatch):
+    """``compaction`` forces one of the two ordered-compaction kernels (None: the library's own choice, which is
+    one CTA per image from 128 images on)."""
     from dusty_gan_b200.models.dusty import DUSty1, DUSty2
     from dusty_gan_b200 import pipeline
+    if compaction:
+        monkeypatch.setenv("DUSTY_HEAD_COMPACT", compaction)
     B, H, W = shape
     depth, conf, u1, u2 = head_inputs(B, kind, H, W, 42 + kind, "cuda")
     head = (DUSty1 if kind == 1 else DUSty2)(torch.nn.Identity(), tau=1.0).cuda().eval()
