@@ -572,12 +572,20 @@ static_assert(MT_SMEM_BYTES >= CELLS * 4, "the cell counters alias the box/recor
 
 struct MtRec { float maxT; int e; float x, y, z; float pad0, pad1, pad2; };   // 32 B
 struct MtWin { unsigned val; int e; float x, y, z; };
+// CHIP variant: the running distances of the first MT_DCAP eligible points live in shared memory (64 KB), three
+// clouds per SM. Only the read-only coordinates of a touched bucket then travel from L2, and the clouds in flight
+// (444 x 15.6 k points x 12 B = 83 MB) fit the 126 MB L2: the six-clouds-per-SM layout keeps 277 MB of coordinates,
+// distances and indices in flight and pays 13 GB of DRAM traffic per 888 clouds for it (profiles/SUMMARY_r1.md).
+constexpr int MT_DCAP = 14336;                   // 56 KB of distances + 17 KB of boxes/records: three clouds per SM
+constexpr int MT_CHIP_SMEM_BYTES = MT_SMEM_BYTES - MT_ELIST * 4 + MT_DCAP * 4;      // no winner list: picks go straight to idx[]
 
 // comp layout per cloud: x[n128] y[n128] z[n128] oidx[n128]; dist_all: t[n128]
-__global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __restrict__ xyz_all, int n, int m,
+template <bool CHIP>
+__global__ void __launch_bounds__(MT_TPB, CHIP ? 3 : 6) fps_multi_kernel(const float* __restrict__ xyz_all, int n, int m,
                                                               int* __restrict__ idx_all, float* __restrict__ out_all,
                                                               float* __restrict__ comp_all, float* __restrict__ dist_all) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  float* const sdist = reinterpret_cast<float*>(smraw + MT_SMEM_BYTES - MT_ELIST * 4);      // CHIP only: distances of points [0, MT_DCAP), in place of the winner list
   int* const cells = reinterpret_cast<int*>(smraw);
   float4* const blo = reinterpret_cast<float4*>(smraw);
   float4* const bhi = blo + MT_BUCKETS;
@@ -682,13 +690,15 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
       const float mag = fmaf(z, z, fmaf(x, x, y * y));
       if (!((double)mag <= 1e-3)) {
         const int e = atomicAdd(&cells[cell_of(x, y, z)], 1);
-        *at(e, 0) = x; *at(e, 1) = y; *at(e, 2) = z; *at(e, 3) = 1e10f; *reinterpret_cast<int*>(at(e, 4)) = k;
+        *at(e, 0) = x; *at(e, 1) = y; *at(e, 2) = z; *reinterpret_cast<int*>(at(e, 4)) = k;
+        if (CHIP && e < MT_DCAP) sdist[e] = 1e10f; else *at(e, 3) = 1e10f;
       }
     }
     const int E_pad = (E + BUCKET - 1) / BUCKET * BUCKET;
     if (tid < E_pad - E) {
       const int e = E + tid;
-      *at(e, 0) = 0.f; *at(e, 1) = 0.f; *at(e, 2) = 0.f; *at(e, 3) = -1.0f; *reinterpret_cast<int*>(at(e, 4)) = 0;
+      *at(e, 0) = 0.f; *at(e, 1) = 0.f; *at(e, 2) = 0.f; *reinterpret_cast<int*>(at(e, 4)) = 0;
+      if (CHIP && e < MT_DCAP) sdist[e] = -1.0f; else *at(e, 3) = -1.0f;
     }
     __threadfence_block();
     __syncthreads();                     // cell counters are dead: the region becomes boxes + records
@@ -742,14 +752,34 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
 
       // (b) update the buckets that may change
       const f32x2 c2x = pack2(ccx, ccx), c2y = pack2(ccy, ccy), c2z = pack2(ccz, ccz);
+      // The coordinates of a touched bucket come from L2: while one bucket is processed the next one's three
+      // 128-bit loads are already in flight (a warp touches 0-3 buckets per iteration).
+      float4 nx = make_float4(0, 0, 0, 0), ny = nx, nz = nx;
+      if (CHIP && need != 0u) {
+        const float* const nb0 = cb + ((__ffs(need) - 1) * MT_NW + warp) * (5 * BUCKET) + 4 * lane;
+        nx = *reinterpret_cast<const float4*>(nb0);
+        ny = *reinterpret_cast<const float4*>(nb0 + BUCKET);
+        nz = *reinterpret_cast<const float4*>(nb0 + 2 * BUCKET);
+      }
       for (unsigned todo = need; todo != 0u; todo &= todo - 1u) {
         const int b = (__ffs(todo) - 1) * MT_NW + warp;
         const int e0 = b * BUCKET + 4 * lane;
         float* const pb = cb + b * (5 * BUCKET) + 4 * lane;
-        const float4 px = *reinterpret_cast<const float4*>(pb);
-        const float4 py = *reinterpret_cast<const float4*>(pb + BUCKET);
-        const float4 pz = *reinterpret_cast<const float4*>(pb + 2 * BUCKET);
-        const float4 t4 = *reinterpret_cast<const float4*>(pb + 3 * BUCKET);
+        float4 px = nx, py = ny, pz = nz;
+        if (!CHIP) {
+          px = *reinterpret_cast<const float4*>(pb);
+          py = *reinterpret_cast<const float4*>(pb + BUCKET);
+          pz = *reinterpret_cast<const float4*>(pb + 2 * BUCKET);
+        }
+        const unsigned rest = todo & (todo - 1u);
+        if (CHIP && rest != 0u) {
+          const float* const nb1 = cb + ((__ffs(rest) - 1) * MT_NW + warp) * (5 * BUCKET) + 4 * lane;
+          nx = *reinterpret_cast<const float4*>(nb1);
+          ny = *reinterpret_cast<const float4*>(nb1 + BUCKET);
+          nz = *reinterpret_cast<const float4*>(nb1 + 2 * BUCKET);
+        }
+        float* const tp = (CHIP && e0 < MT_DCAP) ? sdist + e0 : pb + 3 * BUCKET;        // warp-uniform choice
+        const float4 t4 = *reinterpret_cast<const float4*>(tp);
         const f32x2 dx0 = sub2(pack2(px.x, px.y), c2x), dx1 = sub2(pack2(px.z, px.w), c2x);
         const f32x2 dy0 = sub2(pack2(py.x, py.y), c2y), dy1 = sub2(pack2(py.z, py.w), c2y);
         const f32x2 dz0 = sub2(pack2(pz.x, pz.y), c2z), dz1 = sub2(pack2(pz.z, pz.w), c2z);
@@ -759,7 +789,7 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
         unpack2(d0, d[0], d[1]);
         unpack2(d1, d[2], d[3]);
         float tq[4] = {fminf(d[0], t4.x), fminf(d[1], t4.y), fminf(d[2], t4.z), fminf(d[3], t4.w)};
-        *reinterpret_cast<float4*>(pb + 3 * BUCKET) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+        *reinterpret_cast<float4*>(tp) = make_float4(tq[0], tq[1], tq[2], tq[3]);
         const float m4 = fmaxf(fmaxf(tq[0], tq[1]), fmaxf(tq[2], tq[3]));
         const unsigned vb = m4 < 0.f ? 0u : __float_as_uint(m4);
         const unsigned vmax = __reduce_max_sync(0xffffffffu, vb);
@@ -819,11 +849,11 @@ __global__ void __launch_bounds__(MT_TPB, 6) fps_multi_kernel(const float* __res
       ccx = __shfl_sync(0xffffffffu, s2.x, src);
       ccy = __shfl_sync(0xffffffffu, s2.y, src);
       ccz = __shfl_sync(0xffffffffu, s2.z, src);
-      if (tid == 0) { if (j < MT_ELIST) elist[j] = ew; else idx[j] = ew; }
+      if (tid == 0) { if (!CHIP && j < MT_ELIST) elist[j] = ew; else idx[j] = ew; }
     }
     __threadfence_block();
     __syncthreads();
-    for (int j = 1 + tid; j < m; j += MT_TPB) idx[j] = orig(j < MT_ELIST ? elist[j] : idx[j]);
+    for (int j = 1 + tid; j < m; j += MT_TPB) idx[j] = orig((!CHIP && j < MT_ELIST) ? elist[j] : idx[j]);
   }
 
   if (out_all != nullptr) {
@@ -882,25 +912,28 @@ extern "C" int dusty_fps(const float* xyz, int b, int n, int m, int32_t* idx, fl
   // fps_multi_kernel addresses both regions as one (5 n128 floats per cloud): they must be contiguous
   if (temp != comp + (size_t)b * 4 * ((n + 127) / 128 * 128)) return fail_arg(DUSTY_EINVAL, "fps: workspace regions are not contiguous");
   static bool configured[kMaxDevices] = {};
-  static bool force_flat = false, force_single = false, force_multi = false;
+  static bool force_flat = false, force_single = false, force_multi = false, force_l2 = false;
   const int dev = current_device();
   if (!configured[dev]) {
     DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DUSTY_CUDA(cudaFuncSetAttribute(fps_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DUSTY_CUDA(cudaFuncSetAttribute(fps_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
-    DUSTY_CUDA(cudaFuncSetAttribute(fps_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
-    const char* env = getenv("DUSTY_FPS_ALGO");       // A/B switch for profiling: flat | single | multi; same indices from all
+    DUSTY_CUDA(cudaFuncSetAttribute(fps_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(fps_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_CHIP_SMEM_BYTES));
+    const char* env = getenv("DUSTY_FPS_ALGO");       // A/B switch for profiling: flat | single | multi | l2 (six per SM, distances in L2); same indices from all
     force_flat = env && env[0] == 'f';
     force_single = env && env[0] == 's';
     force_multi = env && env[0] == 'm';
+    force_l2 = env && env[0] == 'l';
     configured[dev] = true;
   }
   // more clouds than SMs: four clouds per SM hide each other's latency chain (throughput variant);
   // otherwise one cloud per SM with everything on chip (latency variant)
-  const bool multi = force_multi || (!force_single && b > kNumSMs);
+  const bool multi = force_multi || force_l2 || (!force_single && b > kNumSMs);
   if (n > REG_CAP) fps_flat_kernel<false><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
   else if (force_flat) fps_flat_kernel<true><<<b, TPB, SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
-  else if (multi) fps_multi_kernel<<<b, MT_TPB, MT_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
+  else if (multi && force_l2) fps_multi_kernel<false><<<b, MT_TPB, MT_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
+  else if (multi) fps_multi_kernel<true><<<b, MT_TPB, MT_CHIP_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp, temp);
   else fps_pruned_kernel<<<b, TPB, PR_SMEM_BYTES, st>>>(xyz, n, m, idx, out_xyz, comp);
   DUSTY_AFTER_LAUNCH("fps kernel");
   return 0;

@@ -113,3 +113,25 @@ def test_duplicate_points_tie_inside_one_lane():
     y = lidar_like_clouds(300, 2048, 32, dropped=0.3, near=0.1)   # more clouds than SMs
     y[:, 1::2] = y[:, ::2]                             # pairs of duplicates
     assert np.array_equal(fps_gpu(y, 128), native.fps(y, 128))
+
+
+def kitti_like_dense(clouds, seed):
+    """Un-sampled 64x512 clouds with ~28 k eligible points (|p|^2 > 1e-3), what real KITTI scans give:
+    more than the 17 792 points whose coordinates fit one SM's shared memory and more than the 16 384 running
+    distances the throughput variant keeps on chip."""
+    return lidar_like_clouds(clouds, 32768, seed, dropped=0.12, near=0.03)
+
+
+def test_kitti_like_28k_eligible_points_every_variant(monkeypatch):
+    x = kitti_like_dense(3, 41)
+    elig = ((x.astype(np.float64) ** 2).sum(-1) > 1e-3).sum(1)
+    assert elig.min() > 27000
+    want = native.fps(x, 2048)
+    assert np.array_equal(fps_gpu(x, 2048), want)                      # one cloud per SM, tail of the coordinates in L2
+    ref = refload.load("dustyref_fps")
+    if ref is not None:
+        assert np.array_equal(ref.furthest_point_sampling(cuda(x), 2048).cpu().numpy(), want)
+    many = np.concatenate([x, kitti_like_dense(150, 42)])              # > 148 clouds: three per SM, distances on chip + overflow
+    got = fps_gpu(many, 512)
+    assert np.array_equal(got[:3], native.fps(x, 512))
+    assert np.array_equal(got[3:60], fps_gpu(many[3:60], 512))         # same indices from the one-cloud-per-SM variant
