@@ -54,10 +54,13 @@ struct Params {
   long long ldm;
   // batch front end
   float* dist1; float* dist2;
-  // merged-origin clouds (matrix front end, DUSTY_MATRIX_MERGE_ORIGIN) reuse idx1 / idx2 as the per-cloud
-  // int2 {points kept, weight of the last kept point} tables of the X / Y side: the struct keeps the
-  // size the dense kernel was tuned with (two more parameter words changed ptxas' register allocation)
   int* idx1; int* idx2;
+  // merged-origin clouds (MERGED instantiations): per-cloud {points kept, weight of the last kept point}, the
+  // per-chunk bounding boxes of sorted clouds (null: no pruning) and, for the batch front end, the map from a
+  // sorted position back to the original point index (the merged origin point maps to the first zero point)
+  const int2* metaX; const int2* metaY;
+  const float4* boxX; const float4* boxY;
+  const int* permX; const int* permY;
   // fused MMD/COV/1-NNA epilogue (matrix front end; null: off). keys = 3 arrays of n_total packed
   // (float bits << 32 | stacked index) minima: [0] leave-one-out nearest neighbour of every stacked cloud,
   // [1] nearest reference cloud of every generated cloud, [2] nearest generated cloud of every reference cloud
@@ -95,10 +98,12 @@ __device__ __forceinline__ float search_window(float ax, float ay, float az, flo
 }
 
 // The whole tile (npairs candidate pairs in scan format) against one row point, in the reference's rounding,
-// by all 32 lanes of a warp: minimum and, if wanted, its lowest candidate index (tile-relative).
+// by all 32 lanes of a warp: minimum and, if wanted, the tile-relative position of the winner -- the lowest
+// position among bit-equal minima, or, for sorted clouds (perm != null: position of the tile's first candidate
+// in the map from positions to original indices), the position with the lowest original index.
 template <bool WANT_INDEX>
 __device__ __forceinline__ void warp_tile_exact_min(const float4* tp, int npairs, float ax, float ay, float az, int lane,
-                                                    float& best, int& best_idx) {
+                                                    const int* perm, float& best, int& best_pos) {
   const f32x2 ax2 = pack2(ax, ax), ay2 = pack2(ay, ay), az2 = pack2(az, az);
   float e = __int_as_float(0x7f800000);
   int ei = 0x7fffffff;
@@ -109,9 +114,9 @@ __device__ __forceinline__ void warp_tile_exact_min(const float4* tp, int npairs
     const f32x2 dz = sub2(pack2(q1.x, q1.y), az2);
     float lo, hi;
     unpack2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lo, hi);
-    if (WANT_INDEX) {                       // q ascends: strict < keeps the lane's lowest index
-      if (lo < e) { e = lo; ei = 2 * q; }
-      if (hi < e) { e = hi; ei = 2 * q + 1; }
+    if (WANT_INDEX) {                       // q ascends: strict < keeps the lane's lowest position
+      if (lo < e || (perm && lo == e && ei != 0x7fffffff && perm[2 * q] < perm[ei])) { e = lo; ei = 2 * q; }
+      if (hi < e || (perm && hi == e && ei != 0x7fffffff && perm[2 * q + 1] < perm[ei])) { e = hi; ei = 2 * q + 1; }
     } else {
       e = min3(e, lo, hi);
     }
@@ -120,7 +125,13 @@ __device__ __forceinline__ void warp_tile_exact_min(const float4* tp, int npairs
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
   best = m;
-  if (WANT_INDEX) best_idx = (int)__reduce_min_sync(0xffffffffu, e == m ? (unsigned)ei : 0x7fffffffu);
+  if (WANT_INDEX) {
+    const bool mine = e == m && ei != 0x7fffffff;
+    const unsigned key = mine ? (unsigned)(perm ? perm[ei] : ei) : 0x7fffffffu;
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+    const unsigned who = __ballot_sync(0xffffffffu, mine && key == kmin);
+    best_pos = who ? __shfl_sync(0xffffffffu, ei, __ffs(who) - 1) : 0x7fffffff;
+  }
 }
 
 // NT threads per CTA. The register tile of R = 8 rows per thread is what makes the search FMA-bound
@@ -138,8 +149,8 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   // and the box of each warp's rows; dist1 / dist2 carry the X / Y side box tables (null: no pruning)
   __shared__ float4 sbox[MERGED ? 2 * 2 * (TILE / CHUNK) : 1];
   __shared__ float4 wbox[MERGED ? 2 * (NT / 32) : 1];
-  const float4* const bxX = MERGED ? reinterpret_cast<const float4*>(p.dist1) : nullptr;
-  const float4* const bxY = MERGED ? reinterpret_cast<const float4*>(p.dist2) : nullptr;
+  const float4* const bxX = MERGED ? p.boxX : nullptr;
+  const float4* const bxY = MERGED ? p.boxY : nullptr;
   const bool prune = MERGED && bxX != nullptr;
 
   constexpr int RB = NT * R;
@@ -161,8 +172,9 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
     ci = cj = blockIdx.y;
     dir_only = blockIdx.z;
     rb_only = blockIdx.x;
-    const int nrb = ((dir_only == 0 ? p.countX : p.countY) + RB - 1) / RB;
-    if (rb_only >= nrb) return;
+    int rows_here = dir_only == 0 ? p.countX : p.countY;
+    if (MERGED) rows_here = (dir_only == 0 ? p.metaX[ci] : p.metaY[cj]).x;
+    if (rb_only >= (rows_here + RB - 1) / RB) return;
   }
   const float4* const sx = p.scanX + (long long)ci * p.strideX;
   const float4* const sy = p.scanY + (long long)cj * p.strideY;
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   // points actually scanned per cloud; with merged origins the last one stands for `wlast` identical
   // (0,0,0) points of the original cloud (means still divide by the full count)
   int2 mx = make_int2(p.countX, 1), my = make_int2(p.countY, 1);
-  if (MERGED) { mx = reinterpret_cast<const int2*>(p.idx1)[ci]; my = reinterpret_cast<const int2*>(p.idx2)[cj]; }
+  if (MERGED) { mx = p.metaX[ci]; my = p.metaY[cj]; }
 // Merged clouds have arbitrary point counts, so the last row block of a direction is usually almost empty
 // (16 390 points = 8 full blocks + 6 rows). There a warp owns 32 R consecutive rows, and a warp without
 // live rows skips the search: the FMA pipe it would have occupied goes to the SM's other resident CTA.
@@ -228,6 +240,13 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   };
   if (tid == 0) issue(pos_begin, 0);
 
+  // Batch front end on sorted clouds: a candidate's position is not its index. Ties between bit-equal distances go
+  // to the lowest ORIGINAL index (the reference's rule), looked up only when a tie actually occurs.
+  auto before = [&](int dir, int posA, int posB) -> bool {
+    if (!MERGED) return posA < posB;
+    const int* pm = dir == 0 ? p.permY + (long long)cj * p.strideY : p.permX + (long long)ci * p.strideX;
+    return pm[posA] < pm[posB];
+  };
   f32x2 nax[R], nay[R], naz[R];     // {-2a, -2a}: search operands; ptxas folds the pair into FFMA2's scalar-broadcast form
   float eb[R];                      // exact running minimum over tiles
   int ei[R];                        // its index (batch front end only)
@@ -311,7 +330,8 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           const float gx = max3(0.0f, bl.x - rh.x, rl.x - bh.x);
           const float gy = max3(0.0f, bl.y - rh.y, rl.y - bh.y);
           const float gz = max3(0.0f, bl.z - rh.z, rl.z - bh.z);
-          visit = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))) < ubmax;
+          const float lb = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy)));
+          visit = MATRIX ? lb < ubmax : lb <= ubmax;      // arg-mins: a chunk that can only TIE may still hold the lower index
         }
         part[h] = __ballot_sync(0xffffffffu, visit);
       }
@@ -382,9 +402,9 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           if (MATRIX) {
             e[r] = min3(e[r], lo, hi);
           } else {
-            const int i0 = t * TILE + cid[g + r] * CH + 2 * kk;
-            if (lo < e[r] || (lo == e[r] && i0 < eidx[r])) { e[r] = lo; eidx[r] = i0; }
-            if (hi < e[r] || (hi == e[r] && i0 + 1 < eidx[r])) { e[r] = hi; eidx[r] = i0 + 1; }
+            const int i0 = te * TILE + cid[g + r] * CH + 2 * kk;
+            if (lo < e[r] || (lo == e[r] && (eidx[r] == 0x7fffffff || before(dir, i0, eidx[r])))) { e[r] = lo; eidx[r] = i0; }
+            if (hi < e[r] || (hi == e[r] && (eidx[r] == 0x7fffffff || before(dir, i0 + 1, eidx[r])))) { e[r] = hi; eidx[r] = i0 + 1; }
           }
         }
       }
@@ -392,8 +412,8 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
       for (int r = 0; r < G; ++r) {
         if (MATRIX) {
           eb[g + r] = fminf(eb[g + r], e[r]);
-        } else if (e[r] < eb[g + r]) {            // tiles ascend: the lowest index keeps ties
-          eb[g + r] = e[r];
+        } else if (e[r] < eb[g + r] || (MERGED && e[r] == eb[g + r] && eidx[r] != 0x7fffffff && before(dir, eidx[r], ei[g + r]))) {
+          eb[g + r] = e[r];                        // dense clouds: tiles ascend, so the lowest index keeps ties by itself
           ei[g + r] = eidx[r];
         }
       }
@@ -413,14 +433,16 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           flagged &= flagged - 1;
           float m;
           int mi = 0;
+          const int* tile_perm = nullptr;
+          if (MERGED && !MATRIX) tile_perm = (dir == 0 ? p.permY + (long long)cj * p.strideY : p.permX + (long long)ci * p.strideX) + te * TILE;
           warp_tile_exact_min<!MATRIX>(tp, nch * PR, __shfl_sync(0xffffffffu, ax, src), __shfl_sync(0xffffffffu, ay, src),
-                                       __shfl_sync(0xffffffffu, az, src), lane, m, mi);
+                                       __shfl_sync(0xffffffffu, az, src), lane, tile_perm, m, mi);
           if (lane == src) {
             if (MATRIX) {
               eb[r] = fminf(eb[r], m);
-            } else {
-              mi += t * TILE;
-              if (m < eb[r] || (m == eb[r] && mi < ei[r])) { eb[r] = m; ei[r] = mi; }
+            } else if (mi != 0x7fffffff) {
+              mi += te * TILE;
+              if (m < eb[r] || (m == eb[r] && before(dir, mi, ei[r]))) { eb[r] = m; ei[r] = mi; }
             }
           }
         }
@@ -441,9 +463,15 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           } else {
             float* dist = dir == 0 ? p.dist1 : p.dist2;
             int* idx = dir == 0 ? p.idx1 : p.idx2;
-            const long long o = (long long)ci * rowcount + row;
-            dist[o] = eb[r];
-            if (idx) idx[o] = ei[r] == 0x7fffffff ? 0 : ei[r];
+            if (MERGED) {      // per sorted position (stride = padded count); scattered to the original order afterwards
+              const long long o = (long long)ci * (dir == 0 ? p.strideX : p.strideY) + row;
+              dist[o] = eb[r];
+              idx[o] = (dir == 0 ? p.permY + (long long)cj * p.strideY : p.permX + (long long)ci * p.strideX)[ei[r] == 0x7fffffff ? 0 : ei[r]];
+            } else {
+              const long long o = (long long)ci * rowcount + row;
+              dist[o] = eb[r];
+              if (idx) idx[o] = ei[r] == 0x7fffffff ? 0 : ei[r];
+            }
           }
         }
       }
@@ -576,10 +604,17 @@ __device__ __forceinline__ unsigned spread7(unsigned v) {          // abcdefg ->
 
 __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __restrict__ xyz, int count, long long stride,
                                                              float4* __restrict__ out, int2* __restrict__ meta,
-                                                             float4* __restrict__ boxes, int boxstride) {
+                                                             float4* __restrict__ boxes, int boxstride,
+                                                             int* __restrict__ perm_all, int* __restrict__ inv_all) {
   extern __shared__ unsigned keys[];            // n2 keys (next power of two >= count)
   __shared__ float red[SORT_TPB / 32][6];
   __shared__ int wsum[SORT_TPB / 32];
+  __shared__ int first_zero;
+  // batch front end only: perm[position] = original index (the merged origin point stands for the FIRST zero point,
+  // the arg-min the reference reports among equal distances), inv[original index] = position
+  int* const perm = perm_all ? perm_all + blockIdx.x * stride : nullptr;
+  int* const inv = inv_all ? inv_all + (long long)blockIdx.x * count : nullptr;
+  if (threadIdx.x == 0) first_zero = 0x7fffffff;
   const long long c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* src = xyz + c * count * 3;
@@ -600,6 +635,7 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
       hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
     }
   }
+  __syncthreads();                              // first_zero is initialised
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -653,6 +689,12 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
     }
   }
 
+  if (inv != nullptr) {                         // zero points: all stand behind the one origin point
+    for (int i = tid; i < count; i += SORT_TPB) {
+      if (src[3 * i] == 0.0f && src[3 * i + 1] == 0.0f && src[3 * i + 2] == 0.0f) { inv[i] = total; atomicMin(&first_zero, i); }
+    }
+    __syncthreads();
+  }
   // ---- sorted points in scan format + one origin point + NaN padding; a box per 32-candidate chunk ----
   const int zeros = count - total;
   const int kept = total + (zeros > 0 ? 1 : 0);
@@ -665,8 +707,12 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
       const int i = (int)(keys[pos] & 0x7fffu);
       x = src[3 * i]; y = src[3 * i + 1]; z = src[3 * i + 2];
       n = fmaf(z, z, fmaf(x, x, y * y));
+      if (perm) { perm[pos] = i; inv[i] = pos; }
     } else if (pos == total && zeros > 0) {
       x = y = z = n = 0.0f;
+      if (perm) perm[pos] = first_zero;
+    } else if (perm) {
+      perm[pos] = 0;
     }
     float* q = dst + (size_t)(pos >> 1) * 8 + (pos & 1);     // {x0,x1,y0,y1}{z0,z1,n0,n1}
     q[0] = x; q[2] = y; q[4] = z; q[6] = n;
@@ -808,7 +854,20 @@ static int run_prep_merge(const float* xyz, long long clouds, int count, float4*
 
 static size_t box_bytes(long long clouds, int count) { return align_up((size_t)clouds * (padded_of(count) / CHUNK) * 32, 256); }
 
-static int run_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st) {
+// (clouds, count) results at sorted positions -> the original point order (batch front end on sorted clouds)
+__global__ void __launch_bounds__(256) unsort_kernel(const float* __restrict__ dist_sorted, const int* __restrict__ idx_sorted,
+                                                     const int* __restrict__ inv, long long clouds, int count, long long stride,
+                                                     float* __restrict__ dist, int* __restrict__ idx) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= clouds * count) return;
+  const long long c = g / count;
+  const long long o = c * stride + inv[g];
+  dist[g] = dist_sorted[o];
+  if (idx) idx[g] = idx_sorted[o];
+}
+
+static int run_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st,
+                         int* perm = nullptr, int* inv = nullptr) {
   if (clouds == 0) return 0;
   int n2 = 1;
   while (n2 < count) n2 <<= 1;
@@ -819,7 +878,7 @@ static int run_prep_sort(const float* xyz, long long clouds, int count, float4* 
     configured[dev] = true;
   }
   prep_sort_kernel<<<(unsigned)clouds, SORT_TPB, (size_t)n2 * 4, st>>>(xyz, count, padded_of(count), out, meta, boxes,
-                                                                        padded_of(count) / CHUNK * 2);
+                                                                        padded_of(count) / CHUNK * 2, perm, inv);
   DUSTY_AFTER_LAUNCH("chamfer prep_sort_kernel");
   return 0;
 }
@@ -830,8 +889,40 @@ static int run_prep_sort(const float* xyz, long long clouds, int count, float4* 
 using namespace dusty;
 using namespace dusty::chamfer;
 
+// Un-sampled clouds in the batch front end (compute_cd on (B, H*W, 3) pairs, reference evaluate_reconstruction.py:
+// 124-131): the same treatment as the matrix front end -- zero points merged into one candidate, kept points
+// Morton-sorted with a box per chunk, chunks pruned by box distance -- plus the maps back to the original order.
+static bool forward_takes_sorted_path(int n, int m) {
+  static const bool enabled = [] { const char* e = getenv("DUSTY_CHAMFER_BATCH_SORT"); return !(e && e[0] == '0'); }();
+  const int big = n > m ? n : m;
+  return enabled && big > 4096 && big <= SORT_CAP;
+}
+
+namespace {
+struct SortedSide {          // workspace of one side of a sorted batch call
+  float4* scan; int2* meta; float4* boxes; int* perm; int* inv; float* dist; int* idx;
+  static size_t bytes(long long b, int count) {
+    const size_t pad = (size_t)b * padded_of(count);
+    return align_up(scan_bytes(b, count), 256) + meta_bytes(b) + box_bytes(b, count) + 3 * align_up(pad * 4, 256) +
+           align_up((size_t)b * count * 4, 256);
+  }
+  char* carve(char* w, long long b, int count) {
+    const size_t pad = (size_t)b * padded_of(count);
+    scan = reinterpret_cast<float4*>(w); w += align_up(scan_bytes(b, count), 256);
+    meta = reinterpret_cast<int2*>(w); w += meta_bytes(b);
+    boxes = reinterpret_cast<float4*>(w); w += box_bytes(b, count);
+    perm = reinterpret_cast<int*>(w); w += align_up(pad * 4, 256);
+    dist = reinterpret_cast<float*>(w); w += align_up(pad * 4, 256);
+    idx = reinterpret_cast<int*>(w); w += align_up(pad * 4, 256);
+    inv = reinterpret_cast<int*>(w); w += align_up((size_t)b * count * 4, 256);
+    return w;
+  }
+};
+}  // namespace
+
 extern "C" size_t dusty_chamfer_forward_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 0;
+  if (forward_takes_sorted_path(n, m)) return SortedSide::bytes(b, n) + SortedSide::bytes(b, m);
   return align_up(scan_bytes(b, n), 256) + align_up(scan_bytes(b, m), 256);
 }
 
@@ -853,6 +944,27 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
   if (workspace_bytes < dusty_chamfer_forward_workspace_bytes(b, n, m))
     return fail_arg(DUSTY_ENOSPACE, "chamfer_forward: workspace %zu < %zu", workspace_bytes,
                     dusty_chamfer_forward_workspace_bytes(b, n, m));
+  if (forward_takes_sorted_path(n, m)) {
+    SortedSide X, Y;
+    Y.carve(X.carve(static_cast<char*>(workspace), b, n), b, m);
+    if (int rc = run_prep_sort(xyz1, b, n, X.scan, X.meta, X.boxes, st, X.perm, X.inv)) return rc;
+    if (int rc = run_prep_sort(xyz2, b, m, Y.scan, Y.meta, Y.boxes, st, Y.perm, Y.inv)) return rc;
+    Params p{};
+    p.scanX = X.scan; p.scanY = Y.scan;
+    p.countX = n; p.countY = m;
+    p.paddedX = padded_of(n); p.paddedY = padded_of(m);
+    p.strideX = p.paddedX; p.strideY = p.paddedY;
+    p.dist1 = X.dist; p.dist2 = Y.dist; p.idx1 = X.idx; p.idx2 = Y.idx;
+    p.metaX = X.meta; p.metaY = Y.meta; p.boxX = X.boxes; p.boxY = Y.boxes; p.permX = X.perm; p.permY = Y.perm;
+    constexpr int R = 4;          // 128-row warps: the row boxes the pruning test uses stay tight (see dusty_chamfer_matrix)
+    const int big = n > m ? n : m;
+    if (int rc = launch_nn<R, false, true>(p, dim3((big + TPB * R - 1) / (TPB * R), b, 2), st)) return rc;
+    unsort_kernel<<<(unsigned)(((long long)b * n + 255) / 256), 256, 0, st>>>(X.dist, X.idx, X.inv, b, n, p.strideX, dist1, idx1);
+    DUSTY_AFTER_LAUNCH("chamfer unsort_kernel");
+    unsort_kernel<<<(unsigned)(((long long)b * m + 255) / 256), 256, 0, st>>>(Y.dist, Y.idx, Y.inv, b, m, p.strideY, dist2, idx2);
+    DUSTY_AFTER_LAUNCH("chamfer unsort_kernel");
+    return 0;
+  }
   float4* s1 = static_cast<float4*>(workspace);
   float4* s2 = reinterpret_cast<float4*>(static_cast<char*>(workspace) + align_up(scan_bytes(b, n), 256));
   if (int rc = run_prep(xyz1, b, n, s1, st)) return rc;
@@ -983,8 +1095,8 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
   p.keys = fk.keys; p.n_total = fk.n_total; p.n_ref = fk.n_ref; p.offX = fk.off_a; p.offY = fk.off_b;
   const dim3 grid(nb, rows, 1);
   if (merge) {
-    p.idx1 = reinterpret_cast<int*>(ma); p.idx2 = reinterpret_cast<int*>(mb);
-    if (sorted) { p.dist1 = reinterpret_cast<float*>(ba); p.dist2 = reinterpret_cast<float*>(bb); }
+    p.metaX = ma; p.metaY = mb;
+    if (sorted) { p.boxX = ba; p.boxY = bb; }
     return dispatch_nn<true, true>(merged_r, p, grid, st);
   }
   return dispatch_matrix(pa > pb ? pa : pb, p, grid, st);

@@ -103,8 +103,13 @@ def test_compute_cd_on_unsampled_pairs():
     from dusty_gan_b200.utils.metrics.distance import chamfer_distance
     a, b = head_clouds(1, 3, 411), head_clouds(1, 3, 412)
     d1, d2 = chamfer_distance(a, b)
-    o1, o2, _, _ = native.chamfer_forward(a.cpu().numpy(), b.cpu().numpy(), rounding="cuda")
+    o1, o2, j1, j2 = native.chamfer_forward(a.cpu().numpy(), b.cpu().numpy(), rounding="cuda")
     assert np.array_equal(d1.cpu().numpy(), o1) and np.array_equal(d2.cpu().numpy(), o2)
+    # arg-mins through the sorted path's maps back to the original order: dropped pixels (zero points) report the
+    # FIRST zero point of the other cloud, as the reference's lowest-index rule does
+    from test_gpu_chamfer import run_forward
+    _, _, i1, i2 = run_forward(a.cpu().numpy(), b.cpu().numpy())
+    assert np.array_equal(i1, j1) and np.array_equal(i2, j2)
     cd = compute_cd(a, b).cpu().numpy()
     want = (o1.astype(np.float64).mean(1) + o2.astype(np.float64).mean(1))
     assert np.all(np.abs(cd - want) <= 4 * ULP * want)
