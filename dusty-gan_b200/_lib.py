@@ -68,6 +68,8 @@ SIGNATURES = {
     "dusty_cov_mmd_1nna_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "dusty_cov_mmd_1nna_finalize": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, c_float_p,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dusty_cov_mmd_knna_finalize": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p]),
     "dusty_jsd_vote": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_int_p, c_float_p, C.c_float,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "dusty_jsd_from_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_float_p, C.c_void_p]),

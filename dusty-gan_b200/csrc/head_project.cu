@@ -62,6 +62,7 @@ __device__ __forceinline__ float gate_value(float logit, int mode, float na, flo
   const float l = mode == DUSTY_NOISE_UNIFORM ? logistic_from_uniform(na, nb, p.eps) : na;
   const float x = __fmul_rn(__fadd_rn(logit, l), p.inv_tau);
   const float soft = __frcp_rn(__fadd_rn(1.0f, expf(-x)));     // == 1.0f / y: both are the correctly rounded quotient
+  if (p.threshold != p.threshold) return soft;               // NaN threshold: GumbelSigmoid(hard=False)
   const float hard = soft > p.threshold ? 1.0f : 0.0f;
   return __fadd_rn(__fsub_rn(hard, soft), soft);
 }

@@ -66,6 +66,41 @@ __global__ void __launch_bounds__(TPB) column_kernel(const float* __restrict__ M
   if (threadIdx.x == 0) nn_label[c] = (all.i < nr) ? 1 : 0;   // label of the nearest neighbour (ref = 1)
 }
 
+// Leave-one-out k-NN vote for k > 1 (_compute_nna, reference cov_mmd_1nna.py:84-90: topk(k, dim=0, largest=False),
+// count of reference labels among the k nearest, pred = count / k >= 0.5). One CTA per stacked column; k rounds of a
+// block arg-min that skips the diagonal and the rows already taken (ties: lowest index). Values are compared as
+// stored: the reference's optional sqrt is monotone, so it cannot change which rows are the k nearest.
+constexpr int KMAX = 64;
+__global__ void __launch_bounds__(TPB) knn_label_kernel(const float* __restrict__ Mrr, const float* __restrict__ Mrg,
+                                                        const float* __restrict__ Mgg, int nr, int ng, int k,
+                                                        int* __restrict__ nn_label) {
+  __shared__ MinIdx sm[TPB / 32];
+  __shared__ int taken[KMAX];
+  const int c = blockIdx.x;
+  const float inf = __int_as_float(0x7f800000);
+  int votes = 0;
+  for (int round = 0; round < k; ++round) {
+    MinIdx best{inf, 0x7fffffff};
+    for (int r = threadIdx.x; r < nr + ng; r += TPB) {
+      if (r == c) continue;
+      bool used = false;
+      for (int t = 0; t < round; ++t) used |= taken[t] == r;
+      if (used) continue;
+      float v;
+      if (c < nr) v = r < nr ? Mrr[(long long)r * nr + c] : Mrg[(long long)c * ng + (r - nr)];
+      else v = r < nr ? Mrg[(long long)r * ng + (c - nr)] : Mgg[(long long)(r - nr) * ng + (c - nr)];
+      best = better(best, MinIdx{v, r});
+    }
+    best = block_argmin(best, sm);
+    if (best.i == 0x7fffffff) break;              // fewer than k other rows
+    votes += best.i < nr ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) taken[round] = best.i;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nn_label[c] = ((float)votes / (float)k >= 0.5f) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(TPB) row_kernel(const float* __restrict__ Mrg, int nr, int ng, float* __restrict__ rowmin) {
   __shared__ MinIdx sm[TPB / 32];
   const int r = blockIdx.x;
@@ -173,6 +208,23 @@ extern "C" int dusty_cov_mmd_1nna_finalize(const float* Mrr, const float* Mrg, c
   DUSTY_AFTER_LAUNCH("metrics column_kernel");
   row_kernel<<<nr, TPB, 0, st>>>(Mrg, nr, ng, rowmin);
   DUSTY_AFTER_LAUNCH("metrics row_kernel");
+  final_kernel<<<1, TPB, 0, st>>>(nr, ng, nn_label, colmin, rowmin, covered, out7);
+  DUSTY_AFTER_LAUNCH("metrics final_kernel");
+  return 0;
+}
+
+extern "C" int dusty_cov_mmd_knna_finalize(const float* Mrr, const float* Mrg, const float* Mgg, int nr, int ng, int k,
+                                          float* out7, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k < 1 || k > KMAX) return fail_arg(DUSTY_EINVAL, "cov_mmd_knna: k=%d must be in [1, %d]", k, KMAX);
+  if (int rc = dusty_cov_mmd_1nna_finalize(Mrr, Mrg, Mgg, nr, ng, out7, workspace, workspace_bytes, stream)) return rc;
+  if (k == 1) return 0;
+  int* nn_label = static_cast<int*>(workspace);          // same scratch layout as the k = 1 call that just ran
+  float* colmin = reinterpret_cast<float*>(nn_label + nr + ng);
+  float* rowmin = colmin + ng;
+  int* covered = reinterpret_cast<int*>(rowmin + nr);
+  knn_label_kernel<<<nr + ng, TPB, 0, st>>>(Mrr, Mrg, Mgg, nr, ng, k, nn_label);
+  DUSTY_AFTER_LAUNCH("metrics knn_label_kernel");
   final_kernel<<<1, TPB, 0, st>>>(nr, ng, nn_label, colmin, rowmin, covered, out7);
   DUSTY_AFTER_LAUNCH("metrics final_kernel");
   return 0;

@@ -71,7 +71,7 @@ class _GumbelSigmoidFn(torch.autograd.Function):
     (reference models/dusty.py:54-57: ``mask_hard - mask_soft.detach() + mask_soft``)."""
 
     @staticmethod
-    def forward(ctx, logits, module, threshold):
+    def forward(ctx, logits, module, threshold, weight=None):
         _lib.require_cuda(logits, "logits")
         if logits.dim() != 4 or logits.shape[1] != 1:
             raise ValueError(f"expected (B,1,H,W) logits, got {tuple(logits.shape)}")
@@ -81,7 +81,8 @@ class _GumbelSigmoidFn(torch.autograd.Function):
         out = torch.empty_like(x)
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            _lib.check(lib.dusty_gumbel_sigmoid(_lib.ptr(x), C.byref(gate), module._inv_tau(), np.float32(threshold),
+            thr = np.float32(threshold) if module.hard else np.float32("nan")      # NaN: the kernel returns the soft mask
+            _lib.check(lib.dusty_gumbel_sigmoid(_lib.ptr(x), C.byref(gate), module._inv_tau(), thr,
                                                 np.float32(module.eps), B, H * W, _lib.ptr(out), _lib.stream_of(x)),
                        "dusty_gumbel_sigmoid")
         ctx.module = module
@@ -95,9 +96,19 @@ class _GumbelSigmoidFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        """Gradient of the soft mask (the straight-through estimator for hard=True; the value itself for
+        hard=False), also with respect to the learnable temperature's weight. Off the evaluate path: torch ops."""
         x, noise = ctx.saved_tensors
-        soft = torch.sigmoid((x + noise) * float(ctx.module._inv_tau()))
-        return grad_out * soft * (1 - soft) * float(ctx.module._inv_tau()), None, None
+        m = ctx.module
+        if m.tau is not None:
+            it = float(m._inv_tau())
+            soft = torch.sigmoid((x + noise) * it)
+            return grad_out * soft * (1 - soft) * it, None, None, None
+        with torch.enable_grad():
+            xin = x.detach().requires_grad_(True)
+            soft = torch.sigmoid((xin + noise) * m._inverse_tau_tensor())
+            gx, gw = torch.autograd.grad(soft, (xin, m.weight), grad_out)
+        return gx, None, None, gw
 
 
 class GumbelSigmoid(nn.Module):
@@ -106,19 +117,29 @@ class GumbelSigmoid(nn.Module):
     def __init__(self, tau: float = 1.0, tau_max: float = 1.0, hard: bool = True, eps: float = 1e-10,
                  pixelwise: bool = True):
         super().__init__()
-        if tau is None:
-            raise NotImplementedError("learnable temperature (tau=None) is not used by any shipped config "
-                                      "(reference configs/model/dusty*_dcgan_eqlr.yaml) and is not built")
-        if not hard:
-            raise NotImplementedError("hard=False is not used on the generate-and-evaluate path")
         self.tau = tau
         self.tau_max = tau_max
         self.hard = hard
         self.eps = eps
+        if self.tau is None:
+            self.weight = nn.Parameter(torch.tensor(0.0))
         self.pixelwise = pixelwise
         self.fixed_noise = None
 
+    def _inverse_tau_tensor(self):
+        """Learnable temperature (reference models/dusty.py:39-41): softplus(weight) + 1/tau_max, a 0-dim tensor."""
+        return torch.nn.functional.softplus(self.weight) + 1.0 / self.tau_max
+
     def _inv_tau(self):
+        if self.tau is None:
+            # the reference multiplies the logits by this f32 tensor; its value is read back once per weight version
+            key = (self.weight._version, self.weight.data_ptr())
+            cached = getattr(self, "_inv_tau_cache", None)
+            if cached is None or cached[0] != key:
+                with torch.no_grad():
+                    cached = (key, np.float32(self._inverse_tau_tensor().item()))
+                object.__setattr__(self, "_inv_tau_cache", cached)
+            return cached[1]
         # ATen's CUDA division by a Python scalar multiplies by the reciprocal, formed in double and
         # rounded to f32 once (SURVEY appendix, trap T2; torch 2.11 div_true_kernel_cuda)
         return np.float32(1.0 / self.tau)
@@ -141,7 +162,7 @@ class GumbelSigmoid(nn.Module):
         return self._logistic_from_uniform(u1, u2)
 
     def forward(self, logits, threshold: float = 0.5):
-        return _GumbelSigmoidFn.apply(logits, self, threshold)
+        return _GumbelSigmoidFn.apply(logits, self, threshold, self.weight if self.tau is None else None)
 
     def extra_repr(self):
         return f"hard={self.hard}, eps={self.eps}"

@@ -164,23 +164,23 @@ def _finalize_device(M_rr, M_rg, M_gg):
 
 
 def _compute_nna(M_rr, M_rg, M_gg, k, sqrt=False):
-    """Leave-one-out k-NN two-sample test (reference cov_mmd_1nna.py:68-106). k=1 without sqrt -- the
-    only configuration any caller uses -- runs on the device kernels."""
-    if k == 1 and not sqrt:
+    """Leave-one-out k-NN two-sample test (reference cov_mmd_1nna.py:68-106) on the device kernels. ``sqrt`` only
+    rescales the distances monotonically (``M.abs().sqrt()``), so the k nearest rows -- and every score -- are the
+    same with or without it; it is accepted for signature compatibility."""
+    if k == 1:
         return _finalize_device(M_rr, M_rg, M_gg)[1]
     N_ref, N_gen = M_rg.shape
-    device = M_rg.device
-    label = torch.cat([torch.ones(N_ref, device=device), torch.zeros(N_gen, device=device)], dim=0)
-    M = torch.cat([torch.cat((M_rr, M_rg), dim=1), torch.cat((M_rg.t(), M_gg), dim=1)], dim=0)
-    M = M.abs().sqrt() if sqrt else M
-    M = M + torch.diag(float("inf") * torch.ones_like(label))
-    _, idx = M.topk(k=k, dim=0, largest=False)
-    count = torch.zeros_like(label)
-    for i in range(0, k):
-        count = count + label.index_select(0, idx[i])
-    pred = (count / k >= 0.5).float()
-    return _nna_scores((pred * label).sum().item(), (pred * (1 - label)).sum().item(),
-                       ((1 - pred) * label).sum().item(), ((1 - pred) * (1 - label)).sum().item(), N_ref + N_gen)
+    M_rr, M_rg, M_gg = M_rr.contiguous(), M_rg.contiguous(), M_gg.contiguous()
+    lib = _lib.load()
+    nbytes = lib.dusty_cov_mmd_1nna_workspace_bytes(N_ref, N_gen)
+    ws = _lib.workspace(nbytes, M_rg.device)
+    out = torch.empty(7, device=M_rg.device, dtype=torch.float32)
+    with torch.cuda.device(M_rg.device):
+        _lib.check(lib.dusty_cov_mmd_knna_finalize(_lib.ptr(M_rr), _lib.ptr(M_rg), _lib.ptr(M_gg), N_ref, N_gen, int(k),
+                                                   _lib.ptr(out), _lib.ptr(ws), nbytes, _lib.stream_of(M_rg)),
+                   "dusty_cov_mmd_knna_finalize")
+    o = [float(v) for v in out.tolist()]
+    return _nna_scores(o[3], o[4], o[5], o[6], N_ref + N_gen)
 
 
 def pairwise_matrices(pcs_gen, pcs_ref):

@@ -182,6 +182,11 @@ DUSTY_API int dusty_symmetric_from_shards(const float* blocks, int shards, int c
 DUSTY_API size_t dusty_cov_mmd_1nna_workspace_bytes(int nr, int ng);
 DUSTY_API int dusty_cov_mmd_1nna_finalize(const float* Mrr, const float* Mrg, const float* Mgg, int nr, int ng,
                                 float* out7, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with a k-nearest-neighbour vote, 1 <= k <= 64 (_compute_nna(k), cov_mmd_1nna.py:84-90): tp/fp/fn/tn come
+ * from pred = (#reference clouds among the k nearest) / k >= 0.5; mmd, mmd-sample and the COV count are unchanged.
+ * The reference's optional sqrt of the distances is monotone and does not change the neighbour sets. */
+DUSTY_API int dusty_cov_mmd_knna_finalize(const float* Mrr, const float* Mrg, const float* Mgg, int nr, int ng, int k,
+                                float* out7, void* workspace, size_t workspace_bytes, void* stream);
 
 /* --------------------------------------------------------------------------------------------
  * JSD between occupancy histograms (next row 8f-2; reference utils/metrics/jsd.py:23-121)
@@ -266,8 +271,10 @@ typedef struct dusty_head_params {
 } dusty_head_params;
 
 /* GumbelSigmoid.forward alone (models/dusty.py:45-59): out = (hard - soft) + soft with
- * soft = 1/(1+exp(-((logit + l) * inv_tau))), hard = soft > threshold. logits/out (b,1,h*w) f32,
- * 16-byte aligned, npix a multiple of 4. */
+ * soft = 1/(1+exp(-((logit + l) * inv_tau))), hard = soft > threshold. A NaN threshold selects the soft output
+ * (GumbelSigmoid(hard=False), models/dusty.py:58-59). inv_tau is f32(1/tau), or for the learnable temperature
+ * (tau=None, :39-41) the f32 value of softplus(weight) + 1/tau_max. logits/out (b,1,h*w) f32, 16-byte aligned,
+ * npix a multiple of 4. */
 DUSTY_API int dusty_gumbel_sigmoid(const float* logits, const dusty_gate* gate, float inv_tau, float threshold,
                          float eps, int b, int npix, float* out, void* stream);
 

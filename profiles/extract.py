@@ -46,14 +46,15 @@ for rep in (f"prof_chamfer_{R}.ncu-rep", f"prof_stages_{R}.ncu-rep"):
     path = os.path.join(ROOT, "gpurun_out", rep)
     if os.path.exists(path):
         kernels += raw(path)
-    elif rep.startswith("prof_chamfer") and R != "r1":      # dense Chamfer kernel unchanged since r1 (identical SASS): keep its capture
-        kernels += [k for k in json.load(open(os.path.join(ROOT, "profiles", "ncu_r1_metrics.json"))) if "nn_kernel" in k["Kernel Name"][0]]
+
 json.dump(kernels, open(os.path.join(ROOT, "profiles", f"ncu_{R}_metrics.json"), "w"), indent=1)
 traffic = {}
 for d in kernels:
     name = d["Kernel Name"][0]
-    key = ("chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0>" in name or "nn_kernel<8, 1>" in name
+    key = ("chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0" in name or "nn_kernel<8, 1>" in name
+           else "chamfer_nn_kernel_batch_sorted_8x32768" if "nn_kernel<4, 0, 1" in name
            else "chamfer_nn_kernel_merged_24x32768" if "nn_kernel" in name
+           else "head_project_dusty1_b256_compact" if "head_project_image" in name
            else "head_project_dusty1_b256" if "head_project" in name
            else "chamfer_prep_sort_24x32768" if "prep_sort" in name
            else "scan_preprocess_256x64x2048" if "scan_preprocess" in name

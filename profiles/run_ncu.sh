@@ -18,6 +18,6 @@ ncu --set full --clock-control none --import-source on -k regex:nn_kernel -s 1 -
 fi
 # 3. head + projection, real-scan preprocess, FPS and the merged-origin Chamfer kernel (last launch of each)
 if [[ $STEPS == *s* ]]; then
-ncu --set full --clock-control none --import-source on -k regex:"head_project_kernel|fps_|scan_preprocess|nn_kernel|prep_sort" -s 5 -c 6 -f \
+ncu --set full --clock-control none --import-source on -k regex:"head_project|fps_|scan_preprocess|nn_kernel|prep_sort" -s 6 -c 9 -f \
     -o gpurun_out/prof_stages_${R} python profiles/stage_driver.py > gpurun_out/prof_stages_${R}.log 2>&1
 fi

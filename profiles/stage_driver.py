@@ -1,7 +1,7 @@
-"""Tiny driver for ncu: the stage kernels at their bench sizes. run_ncu.sh skips the first five matching
-launches (warm-up: head x3, FPS multi, scan preprocess) and captures the next five:
-head+projection (batch 256), scan preprocess (256 scans, full width), FPS pruned (148 clouds),
-FPS multi (888 clouds), merged-origin Chamfer matrix (24 un-sampled clouds)."""
+"""Tiny driver for ncu: the stage kernels at their bench sizes. run_ncu.sh skips the warm-up launches and captures:
+head+projection (batch 256) without and with compaction, scan preprocess (256 scans, full width), FPS pruned
+(148 clouds), FPS throughput variant (888 clouds), sorted/pruned Chamfer matrix (24 un-sampled clouds) with its
+prep_sort, and the sorted batch front end on 8 un-sampled pairs."""
 import os
 import sys
 
@@ -26,16 +26,24 @@ def head256():
     return pipeline.maskout_and_project(head, {"depth": d256, "confidence": c256}, lidar, tol=0.0)
 
 
-# ---- warm-up: five matching launches ----
-head256(); head256()
+def head256c():
+    return pipeline.maskout_and_project(head, {"depth": d256, "confidence": c256}, lidar, tol=0.0, compact=True)
+
+
+# ---- warm-up ----
+head256(); head256(); head256c()
 pts = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0)["points"]
 downsample_point_clouds(pts, 2048)
 preprocess_scans(scans, (64, 2048), 0.9, 120.0, -1)
 torch.cuda.synchronize()
+print("WARMUP_DONE", flush=True)
 # ---- captured ----
 head256()
+head256c()
 preprocess_scans(scans, (64, 2048), 0.9, 120.0, -1)
 downsample_point_clouds(pts[:148].contiguous(), 2048)
 downsample_point_clouds(pts, 2048)
 chamfer_matrix(pts[:24].contiguous())
+from dusty_gan_b200.utils.metrics.distance import chamfer_distance  # noqa: E402
+chamfer_distance(pts[:8].contiguous(), pts[8:16].contiguous())
 torch.cuda.synchronize()

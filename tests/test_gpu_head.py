@@ -224,3 +224,36 @@ def test_inv_to_xyz_and_downsample_are_differentiable_like_the_reference():
     assert pts.grad.sum().item() == pytest.approx(2 * 32 * 3)
     with torch.no_grad():
         assert torch.equal(downsample_point_clouds(pts, 32), sub)
+
+
+def test_learnable_temperature_and_soft_output_match_the_reference_op_chain():
+    """GumbelSigmoid(tau=None) multiplies by softplus(weight) + 1/tau_max (reference models/dusty.py:39-41) and
+    GumbelSigmoid(hard=False) returns the soft mask (:58-59); forward bit-equal to the op chain on this device,
+    gradients (logits and the temperature weight) equal to autograd through it."""
+    from dusty_gan_b200.models.dusty import GumbelSigmoid
+    B, H, W = 3, 16, 64
+    _, conf, u1, u2 = head_inputs(B, 1, H, W, 77, "cuda")
+    for hard in (True, False):
+        gate = GumbelSigmoid(tau=None, tau_max=2.0, hard=hard).cuda()
+        with torch.no_grad():
+            gate.weight.fill_(0.37)
+        gate.fixed_noise = gate._logistic_from_uniform(u1, u2)
+        x = conf.clone().requires_grad_(True)
+        out = gate(x, threshold=0.4)
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+        # the reference's op chain
+        y = conf.clone().requires_grad_(True)
+        wt = gate.weight.detach().clone().requires_grad_(True)
+        it = torch.nn.functional.softplus(wt) + 1.0 / 2.0
+        soft = torch.sigmoid((y + gate.fixed_noise.expand(B, -1, -1, -1)) * it)
+        ref = ((soft > 0.4).float() - soft.detach() + soft) if hard else soft
+        (ref * w).sum().backward()
+        assert_bit_equal(out.detach(), ref.detach(), f"learnable-tau forward, hard={hard}")
+        assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(gate.weight.grad, wt.grad, rtol=1e-4, atol=1e-6)
+    soft_gate = GumbelSigmoid(tau=0.7, hard=False).cuda()
+    soft_gate.fixed_noise = gate.fixed_noise
+    got = soft_gate(conf)
+    want = torch.sigmoid((conf + gate.fixed_noise.expand(B, -1, -1, -1)) / 0.7)
+    assert_bit_equal(got, want, "soft mask, fixed temperature")

@@ -62,7 +62,17 @@ def test_finalize_kernel_against_numpy():
     t = m._compute_cov_mmd(cuda(Mrg))
     assert t["cov"] == cm["cov"] and t["mmd"] == pytest.approx(cm["mmd"], rel=1e-6)
     assert m._compute_nna(cuda(Mrr), cuda(Mrg), cuda(Mgg), 1)["tp"] == nna["tp"]
-    assert m._compute_nna(cuda(Mrr), cuda(Mrg), cuda(Mgg), 3)["tp"] >= 0
+    # k > 1 (and the monotone sqrt option) on the device kernel against the reference's topk formulation
+    label = torch.cat([torch.ones(nr), torch.zeros(ng)]).cuda()
+    M = torch.cat([torch.cat((cuda(Mrr), cuda(Mrg)), 1), torch.cat((cuda(Mrg).t(), cuda(Mgg)), 1)], 0)
+    for k, sqrt in ((3, False), (4, True), (7, False), (64, False)):
+        Mk = (M.abs().sqrt() if sqrt else M) + torch.diag(float("inf") * torch.ones_like(label))
+        _, idx = Mk.topk(k=k, dim=0, largest=False)
+        count = sum(label.index_select(0, idx[i]) for i in range(k))
+        pred = (count / k >= 0.5).float()
+        got = m._compute_nna(cuda(Mrr), cuda(Mrg), cuda(Mgg), k, sqrt=sqrt)
+        assert got["tp"] == (pred * label).sum().item() and got["fp"] == (pred * (1 - label)).sum().item()
+        assert got["fn"] == ((1 - pred) * label).sum().item() and got["tn"] == ((1 - pred) * (1 - label)).sum().item()
 
 
 def test_pairwise_distance_signature():
