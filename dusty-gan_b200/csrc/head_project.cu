@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(TPB, C == 1 ? 8 : 7) head_project_kernel(const
     int base = 0;
     for (int s0 = 0; s0 < seg; s0 += 32) {
       unsigned v = 0x80000000u;
-      if (s0 + lane < seg) { do { v = st[s0 + lane]; } while (!(v & 0x80000000u)); }
+      if (s0 + lane < seg) {               // back off between polls: a spinning warp must not take issue slots and LSU
+        v = st[s0 + lane];                 // bandwidth from the CTAs it is waiting for
+        while (!(v & 0x80000000u)) { __nanosleep(64); v = st[s0 + lane]; }
+      }
       base += (int)__reduce_add_sync(0xffffffffu, v & 0x7fffffffu);
     }
     if (lane == 0) {
@@ -259,6 +262,8 @@ __global__ void __launch_bounds__(TPB, C == 1 ? 8 : 7) head_project_kernel(const
 // valid points through its own shared-memory buffer and writes them with coalesced stores. Used when the batch
 // alone fills the GPU (b >= 128 images); the arithmetic is the same code as above, bit for bit.
 constexpr int IMG_TPB = 512;
+constexpr int IMG_STEP = IMG_TPB * 4;                    // pixels per step
+constexpr int IMG_TABLE_BYTES = 2 * 5 * IMG_STEP * 4;    // two stages of {cos el, sin el, cos az, sin az, noise} tiles (80 KB)
 
 template <int C>
 __global__ void __launch_bounds__(IMG_TPB, 2) head_project_image_kernel(const Args a) {
@@ -266,10 +271,28 @@ __global__ void __launch_bounds__(IMG_TPB, 2) head_project_image_kernel(const Ar
   __shared__ __align__(16) float stage[NWARP * 384];      // per-warp: transpose of 128 points, then its packed points
   __shared__ int istage[NWARP * 128];                     // per-warp: pixel indices of its packed points
   __shared__ int wsum[2][NWARP];
+  __shared__ uint64_t full[2];
+  // The trig table and the (per-pixel, logistic) noise map are L2 resident and shared by all images; loading them
+  // where they are used puts two dependent L2 round trips into every step of a CTA that has only 16 warps. They
+  // are therefore brought in one step ahead by 1-D TMA bulk copies (no registers held across the step).
+  extern __shared__ __align__(128) float tables[];
   const dusty_head_params& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long img = blockIdx.x;
   const int npix = a.npix;
+  const bool noise_tile = a.gp.mode == DUSTY_NOISE_LOGISTIC && a.gp.pstride == 1;
+  auto prefetch_tables = [&](int step) {                 // one thread; stage = step & 1
+    float* dst = tables + (step & 1) * (5 * IMG_STEP);
+    const int first = step * IMG_STEP;
+    const uint32_t bytes = (uint32_t)min(IMG_STEP, npix - first) * 4u;
+    mbar_expect_tx(&full[step & 1], (noise_tile ? 5u : 4u) * bytes);
+    #pragma unroll
+    for (int t = 0; t < 4; ++t) bulk_g2s(dst + t * IMG_STEP, a.trig + (long long)t * npix + first, bytes, &full[step & 1]);
+    if (noise_tile) bulk_g2s(dst + 4 * IMG_STEP, a.gp.a + img * a.gp.bstride + first, bytes, &full[step & 1]);
+  };
+  if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  if (tid == 0) prefetch_tables(0);
   const float* depth = a.depth + img * npix;
   const float* conf0 = a.conf + img * C * npix;
   float* omask0 = a.out_mask + img * C * npix;
@@ -288,6 +311,10 @@ __global__ void __launch_bounds__(IMG_TPB, 2) head_project_image_kernel(const Ar
   for (int it = 0; it < steps; ++it) {
     const int pix = it * (IMG_TPB * 4) + tid * 4;
     const float4 dcur = dv, ccur = cv, c1cur = c1;
+    // every thread is past the previous step's barrier, hence done with the stage that is refilled now
+    if (tid == 0 && it + 1 < steps) prefetch_tables(it + 1);
+    mbar_wait(&full[it & 1], (uint32_t)((it >> 1) & 1));
+    const float* const tab = tables + (it & 1) * (5 * IMG_STEP) + tid * 4;
     const int nxt = pix + IMG_TPB * 4;
     if (it + 1 < steps && nxt < npix) {                   // next step's streaming loads
       dv = ldg_stream(reinterpret_cast<const float4*>(depth + nxt));
@@ -298,7 +325,8 @@ __global__ void __launch_bounds__(IMG_TPB, 2) head_project_image_kernel(const Ar
     float X[4] = {0.f, 0.f, 0.f, 0.f}, Y[4] = {0.f, 0.f, 0.f, 0.f}, Z[4] = {0.f, 0.f, 0.f, 0.f};
     if (pix < npix) {
       float4 na = make_float4(0, 0, 0, 0), nb = na;
-      if (a.gp.mode != DUSTY_NOISE_NONE) na = load_noise(a.gp, a.gp.a, img, pix);
+      if (noise_tile) na = *reinterpret_cast<const float4*>(tab + 4 * IMG_STEP);
+      else if (a.gp.mode != DUSTY_NOISE_NONE) na = load_noise(a.gp, a.gp.a, img, pix);
       if (a.gp.mode == DUSTY_NOISE_UNIFORM) nb = load_noise(a.gp, a.gp.b, img, pix);
       float mp[4] = {gate_value(ccur.x, a.gp.mode, na.x, nb.x, p), gate_value(ccur.y, a.gp.mode, na.y, nb.y, p),
                      gate_value(ccur.z, a.gp.mode, na.z, nb.z, p), gate_value(ccur.w, a.gp.mode, na.w, nb.w, p)};
@@ -326,10 +354,10 @@ __global__ void __launch_bounds__(IMG_TPB, 2) head_project_image_kernel(const Ar
         vbits |= valid ? (1u << q) : 0u;
       }
       stg_stream(reinterpret_cast<float4*>(odepth + pix), make_float4(dout[0], dout[1], dout[2], dout[3]));
-      const float4 ce = *reinterpret_cast<const float4*>(a.trig + pix);
-      const float4 se = *reinterpret_cast<const float4*>(a.trig + npix + pix);
-      const float4 ca = *reinterpret_cast<const float4*>(a.trig + 2 * npix + pix);
-      const float4 sa = *reinterpret_cast<const float4*>(a.trig + 3 * npix + pix);
+      const float4 ce = *reinterpret_cast<const float4*>(tab);
+      const float4 se = *reinterpret_cast<const float4*>(tab + IMG_STEP);
+      const float4 ca = *reinterpret_cast<const float4*>(tab + 2 * IMG_STEP);
+      const float4 sa = *reinterpret_cast<const float4*>(tab + 3 * IMG_STEP);
       const float cev[4] = {ce.x, ce.y, ce.z, ce.w}, sev[4] = {se.x, se.y, se.z, se.w};
       const float cav[4] = {ca.x, ca.y, ca.z, ca.w}, sav[4] = {sa.x, sa.y, sa.z, sa.w};
       #pragma unroll
@@ -523,6 +551,22 @@ extern "C" int dusty_head_project(const dusty_head_params* p, const float* depth
   a.segs_per_image = (a.npix + GROUP - 1) / GROUP;
   const long long ctas = (long long)p->b * a.segs_per_image;
   if (ctas > 0x7fffffffLL) return fail_arg(DUSTY_EINVAL, "head_project: grid too large");
+  // batches that fill the GPU with one CTA per image: no cross-CTA scan at all (DUSTY_HEAD_COMPACT=segment|image forces one)
+  const char* const forced = getenv("DUSTY_HEAD_COMPACT");
+  const int force_path = !forced ? 0 : (forced[0] == 's' ? 1 : (forced[0] == 'i' ? 2 : 0));
+  if (compact && (force_path == 2 || (force_path == 0 && p->b >= 128))) {
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+      DUSTY_CUDA(cudaFuncSetAttribute(head_project_image_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMG_TABLE_BYTES));
+      DUSTY_CUDA(cudaFuncSetAttribute(head_project_image_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMG_TABLE_BYTES));
+      configured[dev] = true;
+    }
+    if (p->conf_channels == 1) head_project_image_kernel<1><<<(unsigned)p->b, IMG_TPB, IMG_TABLE_BYTES, st>>>(a);
+    else head_project_image_kernel<2><<<(unsigned)p->b, IMG_TPB, IMG_TABLE_BYTES, st>>>(a);
+    DUSTY_AFTER_LAUNCH("head_project_image_kernel");
+    return 0;
+  }
   if (compact) {
     if (!workspace || workspace_bytes < dusty_head_project_workspace_bytes(p->b, p->h, p->w))
       return fail_arg(DUSTY_ENOSPACE, "head_project: compaction needs %zu workspace bytes", dusty_head_project_workspace_bytes(p->b, p->h, p->w));
@@ -531,15 +575,6 @@ extern "C" int dusty_head_project(const dusty_head_params* p, const float* depth
     static const bool no_ticket = [] { const char* e = getenv("DUSTY_HEAD_TICKET"); return e && e[0] == '0'; }();   // A/B only
     DUSTY_CUDA(cudaMemsetAsync(workspace, 0, ((size_t)ctas + (size_t)p->b * 32) * sizeof(unsigned), st));
     if (no_ticket) a.ticket = nullptr;
-  }
-  // batches that fill the GPU with one CTA per image: no cross-CTA scan at all (DUSTY_HEAD_COMPACT=segment|image forces one)
-  const char* const forced = getenv("DUSTY_HEAD_COMPACT");
-  const int force_path = !forced ? 0 : (forced[0] == 's' ? 1 : (forced[0] == 'i' ? 2 : 0));
-  if (compact && (force_path == 2 || (force_path == 0 && p->b >= 128))) {
-    if (p->conf_channels == 1) head_project_image_kernel<1><<<(unsigned)p->b, IMG_TPB, 0, st>>>(a);
-    else head_project_image_kernel<2><<<(unsigned)p->b, IMG_TPB, 0, st>>>(a);
-    DUSTY_AFTER_LAUNCH("head_project_image_kernel");
-    return 0;
   }
   if (p->conf_channels == 1) {
     if (compact) head_project_kernel<1, true><<<(unsigned)ctas, TPB, 0, st>>>(a);

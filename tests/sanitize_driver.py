@@ -28,7 +28,10 @@ for kind in (1, 2):
     depth, conf, u1, u2 = head_inputs(3, kind, H, W, 7, "cuda")
     gate = head.gumbel if kind == 1 else head.gumbel_pixel
     gate.fixed_noise = gate._logistic_from_uniform(u1, u2)
-    out = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0, compact=True)
+    for mode in ("segment", "image"):          # both ordered-compaction kernels
+        os.environ["DUSTY_HEAD_COMPACT"] = mode
+        out = pipeline.maskout_and_project(head, {"depth": depth, "confidence": conf}, lidar, tol=0.0, compact=True)
+    os.environ.pop("DUSTY_HEAD_COMPACT")
     pts = downsample_point_clouds(out["points"], 64)
 x = torch.from_numpy(lidar_like_clouds(3, 3000, 5)).cuda()
 for algo in ("single", "multi", "flat"):
@@ -50,6 +53,24 @@ preprocess_scans(scans, (8, 24), want=("xyz", "depth", "mask", "inv", "points"))
 preprocess_scans(scans[..., :3].contiguous(), (8, 96))
 u = torch.from_numpy(lidar_like_clouds(3, 4200, 6, dropped=0.5)).cuda()       # > 1024 kept points: sorted + pruned path
 u[1] = 0
+# round 2: batch front end on sorted clouds (perm / inv maps, unsort), its backward (own + scatter kernels), an
+# adversarial cluster that drives every row through the guard's whole-tile re-evaluation, the fused epilogue with
+# unequal point counts (three launches into one key set), the k-NN vote, the symmetric assembly of row shards
+ua = u.clone().requires_grad_(True)
+e1, e2 = chamfer_distance(ua, torch.flip(u, dims=[0]))
+(e1.sum() + e2.sum()).backward()
+cube = (torch.rand(2, 2300, 3, device="cuda") * 0.05 + torch.tensor([0.7, 0.5, 0.1], device="cuda"))
+print(chamfer_matrix(cube, merge_origin=False))
+chamfer_distance(cube, torch.flip(cube, dims=[0]))
+print(compute_cov_mmd_1nna(gen, ref[:, :200].contiguous(), 512, ("cd",), verbose=False))
+from dusty_gan_b200.utils.metrics import cov_mmd_1nna as M  # noqa: E402
+mats = M.pairwise_matrices(gen, ref)
+print(M._compute_nna(*mats, 3))
+from dusty_gan_b200 import sharding  # noqa: E402
+blocks = torch.stack([chamfer_matrix(gen, None, rows=(r, 5, 2), compact_rows=True, out=torch.zeros(3, 5, device="cuda")) for r in range(2)])
+print(sharding.assemble_symmetric(blocks, 5))
+many = torch.from_numpy(lidar_like_clouds(150, 1500, 8)).cuda()          # > 148 clouds: the on-chip-distance FPS variant
+downsample_point_clouds(many, 24)
 print(chamfer_matrix(u, merge_origin=True))
 print(chamfer_matrix(u, u[:2, :600].contiguous(), merge_origin=True))
 torch.cuda.synchronize()
