@@ -88,6 +88,7 @@ SIGNATURES = {
     "dusty_inv_to_xyz": (C.c_int, [C.POINTER(HeadParams), c_float_p, c_float_p, c_float_p, C.c_void_p]),
     "dusty_scan_preprocess": (C.c_int, [C.POINTER(ScanParams), c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                         c_float_p, C.c_void_p]),
+    "dusty_chamfer_count_pairs": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
     "dusty_probe_fp32_peak": (C.c_int, [C.c_int, c_float_p, C.POINTER(C.c_double), C.c_void_p]),
 }
 

@@ -61,6 +61,7 @@ struct Params {
   const int2* metaX; const int2* metaY;
   const float4* boxX; const float4* boxY;
   const int* permX; const int* permY;
+  unsigned long long* visited;   // measurement only (null: off): (row, candidate) pairs the pruned search really evaluated
   // fused MMD/COV/1-NNA epilogue (matrix front end; null: off). keys = 3 arrays of n_total packed
   // (float bits << 32 | stacked index) minima: [0] leave-one-out nearest neighbour of every stacked cloud,
   // [1] nearest reference cloud of every generated cloud, [2] nearest generated cloud of every reference cloud
@@ -134,20 +135,72 @@ __device__ __forceinline__ void warp_tile_exact_min(const float4* tp, int npairs
   }
 }
 
+// DEFERRED guard (merged clouds): one row point against the whole scanned cloud, read from global memory (L2) in the
+// reference's rounding by all 32 lanes; a lane takes whole 32-candidate chunks and skips those whose box cannot
+// reach `thr`, the exact distance already found in the search's winning chunk (boxes == null: every chunk).
+// Returns the minimum and the winner's position (lowest original index among equal minima when perm != null).
+template <bool WANT_INDEX>
+__device__ __forceinline__ void warp_cloud_exact_min(const float4* cloud, int nchunks, const float4* boxes, float thr,
+                                                     float ax, float ay, float az, int lane, const int* perm, float& best,
+                                                     int& best_pos) {
+  const f32x2 ax2 = pack2(ax, ax), ay2 = pack2(ay, ay), az2 = pack2(az, az);
+  float e = __int_as_float(0x7f800000);
+  int ei = 0x7fffffff;
+  for (int ch = lane; ch < nchunks; ch += 32) {
+    if (boxes != nullptr) {
+      const float4 bl = boxes[2 * ch], bh = boxes[2 * ch + 1];
+      const float gx = max3(0.0f, bl.x - ax, ax - bh.x), gy = max3(0.0f, bl.y - ay, ay - bh.y), gz = max3(0.0f, bl.z - az, az - bh.z);
+      if (fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))) > thr) continue;      // cannot reach (or tie) thr
+    }
+    const float4* cp = cloud + (long long)ch * CHUNK;
+    #pragma unroll 4
+    for (int k = 0; k < CHUNK / 2; ++k) {
+      const float4 q0 = cp[2 * k], q1 = cp[2 * k + 1];
+      const f32x2 dx = sub2(pack2(q0.x, q0.y), ax2);
+      const f32x2 dy = sub2(pack2(q0.z, q0.w), ay2);
+      const f32x2 dz = sub2(pack2(q1.x, q1.y), az2);
+      float lo, hi;
+      unpack2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lo, hi);
+      if (WANT_INDEX) {
+        const int i0 = ch * CHUNK + 2 * k;
+        if (lo < e || (lo == e && ei != 0x7fffffff && (perm ? perm[i0] < perm[ei] : i0 < ei))) { e = lo; ei = i0; }
+        if (hi < e || (hi == e && ei != 0x7fffffff && (perm ? perm[i0 + 1] < perm[ei] : i0 + 1 < ei))) { e = hi; ei = i0 + 1; }
+      } else {
+        e = min3(e, lo, hi);
+      }
+    }
+  }
+  float m = e;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  best = m;
+  if (WANT_INDEX) {
+    const bool mine = e == m && ei != 0x7fffffff;
+    const unsigned key = mine ? (unsigned)(perm ? perm[ei] : ei) : 0x7fffffffu;
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+    const unsigned who = __ballot_sync(0xffffffffu, mine && key == kmin);
+    best_pos = who ? __shfl_sync(0xffffffffu, ei, __ffs(who) - 1) : 0x7fffffff;
+  }
+}
+
 // NT threads per CTA. The register tile of R = 8 rows per thread is what makes the search FMA-bound
 // (one LDS.128 pair feeds 24 FFMA2), so small clouds keep R = 8 and shrink the CTA instead: 2048 rows
 // -> 256 threads, 1024 -> 128, 512 -> 64, 256 -> 32 (the matrix front end's table, pick_shape). Every
 // shape keeps 16 warps of 128 registers per SM; the R < 8 instantiations (batch front end on small
 // batches, odd sizes) trade registers for residency because their CTAs are short.
-template <int R, bool MATRIX, bool MERGED, int NT = TPB>
-__global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_kernel(const Params p) {
+// TL = candidates per shared-memory tile. Pruned launches on sorted clouds use small CTAs with small tiles
+// (NT = 64, TL = 512): pruning is per warp, so in a wide CTA most warps find nothing to scan in a given tile and wait
+// at the tile barrier for the one or two that do (ncu: barrier stall 4.1 warps per issue with 8 warps per CTA);
+// two warps per CTA wait for each other only, and twelve such CTAs fit an SM.
+template <int R, bool MATRIX, bool MERGED, int NT = TPB, int TL = TILE>
+__global__ void __launch_bounds__(NT, NT < TPB && MERGED ? (R >= 8 ? 512 : 640) / NT : (R >= 8 ? 512 / NT : (R == 4 ? 3 : 4))) nn_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* const tiles = reinterpret_cast<float4*>(smem_raw);
   __shared__ uint64_t bars[2];
   __shared__ double red[NT / 32];
   // merged + sorted clouds (prep_sort_kernel): per-chunk bounding boxes of the tile in flight (two buffers)
   // and the box of each warp's rows; dist1 / dist2 carry the X / Y side box tables (null: no pruning)
-  __shared__ float4 sbox[MERGED ? 2 * 2 * (TILE / CHUNK) : 1];
+  __shared__ float4 sbox[MERGED ? 2 * 2 * (TL / CHUNK) : 1];
   __shared__ float4 wbox[MERGED ? 2 * (NT / 32) : 1];
   const float4* const bxX = MERGED ? p.boxX : nullptr;
   const float4* const bxY = MERGED ? p.boxY : nullptr;
@@ -156,7 +209,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   constexpr int RB = NT * R;
   // candidates per search chunk = the window the exact pass re-evaluates per row and tile. Small clouds (the
   // shrunken CTAs) take 16: the exact pass is a fixed cost per row, 14 % of the search at 512 points with 32.
-  constexpr int CH = NT < TPB ? CHUNK / 2 : CHUNK;
+  constexpr int CH = (NT < TPB && !MERGED) ? CHUNK / 2 : CHUNK;      // merged clouds: one bounding box per 32 candidates
   constexpr int PR = CH / 2;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -192,7 +245,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
 #define K_paddedX (MERGED ? (mx.x + CHUNK - 1) / CHUNK * CHUNK : p.paddedX)
 #define K_paddedY (MERGED ? (my.x + CHUNK - 1) / CHUNK * CHUNK : p.paddedY)
 
-  const int ntX = (K_paddedX + TILE - 1) / TILE, ntY = (K_paddedY + TILE - 1) / TILE;
+  const int ntX = (K_paddedX + TL - 1) / TL, ntY = (K_paddedY + TL - 1) / TL;
   const int nrbX = (K_countX + RB - 1) / RB, nrbY = (K_countY + RB - 1) / RB;
   const int seg0 = nrbX * ntY;
   int pos_begin, pos_end;
@@ -202,7 +255,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
 
   // the two tile buffers are as large as the largest tile of this launch (launch_nn sizes the dynamic shared
   // memory the same way): small clouds leave room for more resident CTAs to hide the per-entry prologue
-  const int tstride = (R >= 8 && NT == TPB) ? TILE : min(TILE, max(p.paddedX, p.paddedY));
+  const int tstride = (R >= 8 && NT == TPB) ? TL : min(TL, max(p.paddedX, p.paddedY));
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncthreads();
 
@@ -223,16 +276,16 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
       if (pos < seg0) { dir = 0; rb = pos / ntY; t = pos - rb * ntY; } else { dir = 1; const int q = pos - seg0; rb = q / ntX; t = q - rb * ntX; }
       t = tile_of(dir, rb, t);
     }
-    const float4* src = (dir == 0 ? sy : sx) + (long long)t * TILE;
+    const float4* src = (dir == 0 ? sy : sx) + (long long)t * TL;
     const int padded = dir == 0 ? K_paddedY : K_paddedX;
-    const int npts = min(TILE, padded - t * TILE);
+    const int npts = min(TL, padded - t * TL);
     if (MERGED && prune) {
       const float4* bsrc = (dir == 0 ? bxY + (long long)cj * (p.paddedY / CHUNK * 2) : bxX + (long long)ci * (p.paddedX / CHUNK * 2)) +
-                           t * (TILE / CHUNK * 2);
+                           t * (TL / CHUNK * 2);
       const uint32_t bbytes = (uint32_t)(npts / CHUNK) * 32u;
       mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u + bbytes);
       bulk_g2s(tiles + buf * tstride, src, (uint32_t)npts * 16u, &bars[buf]);
-      bulk_g2s(sbox + buf * (2 * (TILE / CHUNK)), bsrc, bbytes, &bars[buf]);
+      bulk_g2s(sbox + buf * (2 * (TL / CHUNK)), bsrc, bbytes, &bars[buf]);
       return;
     }
     mbar_expect_tx(&bars[buf], (uint32_t)npts * 16u);
@@ -250,6 +303,11 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
   f32x2 nax[R], nay[R], naz[R];     // {-2a, -2a}: search operands; ptxas folds the pair into FFMA2's scalar-broadcast form
   float eb[R];                      // exact running minimum over tiles
   int ei[R];                        // its index (batch front end only)
+  // search state: best and runner-up chunk minima of |b|^2 - 2 a.b and the best chunk's number. Dense clouds
+  // restart it for every tile (the exact pass follows the tile); merged clouds carry it across all tiles of a row
+  // block and defer the exact pass to the end (see DEFERRED below), an[] = |a|^2 turns it into a distance bound.
+  float cur[R], sec[R], an[R];
+  int cid[R];
   double dsum = 0.0, S0 = 0.0;
 
   for (int pos = pos_begin; pos < pos_end; ++pos) {
@@ -277,6 +335,10 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
         naz[r] = pack2(mz, mz);
         eb[r] = __int_as_float(0x7f800000);
         ei[r] = 0;
+        if (MERGED) {
+          cur[r] = sec[r] = __int_as_float(0x7f800000); cid[r] = 0;
+          an[r] = 0.25f * fmaf(mz, mz, fmaf(mx, mx, my * my));
+        }
       }
       if (MERGED && prune) {            // bounding box of this warp's live rows (a = -0.5 * (-2a) exactly)
         const float inf = __int_as_float(0x7f800000);
@@ -305,7 +367,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
     mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
     const float4* const tp = tiles + buf * tstride;
     const int te = MERGED ? tile_of(dir, rb, t) : t;     // which tile of the scanned cloud this buffer holds
-    const int nch = min(TILE, scanpadded - te * TILE) / CH;
+    const int nch = min(TL, scanpadded - te * TL) / CH;
 
     if (!MERGED || rb * RB + (tid >> 5) * (32 * R) < rowcount) {      // warp-uniform
     // ---- pruning (merged + sorted clouds): chunks whose box is no closer to the box of this warp's rows than
@@ -314,12 +376,20 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
     //      LB <= d(a,b) in floating point for every row a of the warp and candidate b of the chunk.
     unsigned long long vmask = ~0ull;
     if (MERGED && prune) {
+      // DEFERRED: no exact minimum exists yet; cur + |a|^2 estimates the best candidate's distance within the search's
+      // rounding error u (21 |a|^2 + 15 D) (search_window), the reference formula adds 5 u D: 64 u (|a|^2 + D) on top
+      // is a rigorous upper bound of the row's final (exact) minimum, hence of anything a chunk must beat or tie.
       float m = 0.0f;
       #pragma unroll
-      for (int r = 0; r < R; ++r) if (K_ROW(r) < rowcount) m = fmaxf(m, eb[r]);
-      const float ubmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));   // distances are >= 0
+      for (int r = 0; r < R; ++r) {
+        if (K_ROW(r) < rowcount) {
+          const float dest = fmaxf(cur[r] + an[r], 0.0f);
+          m = fmaxf(m, fmaf(3.81469727e-6f /* 64 * 2^-24 */, an[r] + dest, dest) + 1e-36f);
+        }
+      }
+      const float ubmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));   // >= 0; +inf before the first tile
       const float4 rl = wbox[2 * (tid >> 5)], rh = wbox[2 * (tid >> 5) + 1];
-      const float4* const sb = sbox + buf * (2 * (TILE / CHUNK));
+      const float4* const sb = sbox + buf * (2 * (TL / CHUNK));
       unsigned part[2];
       #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -331,19 +401,47 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           const float gy = max3(0.0f, bl.y - rh.y, rl.y - bh.y);
           const float gz = max3(0.0f, bl.z - rh.z, rl.z - bh.z);
           const float lb = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy)));
-          visit = MATRIX ? lb < ubmax : lb <= ubmax;      // arg-mins: a chunk that can only TIE may still hold the lower index
+          visit = lb <= ubmax;      // a chunk that can only TIE the minimum may still hold the lower index (batch front end)
         }
         part[h] = __ballot_sync(0xffffffffu, visit);
       }
       vmask = (unsigned long long)part[0] | ((unsigned long long)part[1] << 32);
     }
     // ---- search: which chunk of this tile holds the smallest |b|^2 - 2 a.b ----
-    float cur[R], sec[R];
-    int cid[R];
-    #pragma unroll
-    for (int r = 0; r < R; ++r) { cur[r] = sec[r] = __int_as_float(0x7f800000); cid[r] = 0; }
+    if (!MERGED) {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) { cur[r] = sec[r] = __int_as_float(0x7f800000); cid[r] = 0; }
+    }
+    const int cbase = MERGED ? te * (TL / CH) : 0;      // merged clouds number their chunks through the whole cloud
+    // second pruning level (sorted clouds): a chunk that passed the box-to-box test is scanned only if SOME row of the
+    // warp can still gain from it -- the row's own distance to the chunk's box (the same monotone formula, a point
+    // being a degenerate box) against the row's own bound: one far-away row no longer opens the chunk for all 32 R rows
+    float ubr[R];
+    if (MERGED && prune) {
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float dest = fmaxf(cur[r] + an[r], 0.0f);
+        ubr[r] = K_ROW(r) < rowcount ? fmaf(3.81469727e-6f, an[r] + dest, dest) + 1e-36f : -1.0f;      // dead rows never ask
+      }
+    }
+    int nvis = 0;
     for (int c = 0; c < nch; ++c) {
       if (MERGED && !((vmask >> c) & 1ull)) continue;      // warp-uniform
+      if (MERGED && prune) {
+        const float4* const sb = sbox + buf * (2 * (TL / CHUNK));
+        const float4 bl = sb[2 * c], bh = sb[2 * c + 1];
+        bool need = false;
+        #pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float ax, ay, az, dummy;
+          unpack2(nax[r], ax, dummy); unpack2(nay[r], ay, dummy); unpack2(naz[r], az, dummy);
+          ax *= -0.5f; ay *= -0.5f; az *= -0.5f;
+          const float gx = max3(0.0f, bl.x - ax, ax - bh.x), gy = max3(0.0f, bl.y - ay, ay - bh.y), gz = max3(0.0f, bl.z - az, az - bh.z);
+          need |= fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))) <= ubr[r];
+        }
+        if (!__any_sync(0xffffffffu, need)) continue;      // warp-uniform
+      }
+      ++nvis;
       const float4* cp = tp + c * CH;
       float cm[R];
       #pragma unroll
@@ -366,13 +464,17 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
         const bool better = cm[r] < cur[r];     // strict: the earliest chunk keeps bit-equal minima
         sec[r] = fminf(sec[r], better ? cur[r] : cm[r]);      // runner-up: the smallest minimum of any other chunk
         cur[r] = better ? cm[r] : cur[r];
-        cid[r] = better ? c : cid[r];
+        cid[r] = better ? cbase + c : cid[r];
       }
     }
 
+    if (MERGED && p.visited != nullptr && lane == 0) {          // bench.py's executed-flop count for pruned workloads
+      const int first = rb * RB + (tid >> 5) * (32 * R);
+      atomicAdd(p.visited, (unsigned long long)nvis * CH * (unsigned long long)min(32 * R, rowcount - first));
+    }
     // ---- exact: re-evaluate the winning chunk with the reference's rounding ----
     constexpr int G = R < 4 ? R : 4;
-    if (!MERGED || vmask != 0ull)         // nothing scanned in this tile: nothing to re-evaluate
+    if (!MERGED)                          // merged clouds: once per row block, after the last tile (DEFERRED)
     #pragma unroll
     for (int g = 0; g < R; g += G) {
       float e[G];
@@ -402,7 +504,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           if (MATRIX) {
             e[r] = min3(e[r], lo, hi);
           } else {
-            const int i0 = te * TILE + cid[g + r] * CH + 2 * kk;
+            const int i0 = te * TL + cid[g + r] * CH + 2 * kk;
             if (lo < e[r] || (lo == e[r] && (eidx[r] == 0x7fffffff || before(dir, i0, eidx[r])))) { e[r] = lo; eidx[r] = i0; }
             if (hi < e[r] || (hi == e[r] && (eidx[r] == 0x7fffffff || before(dir, i0 + 1, eidx[r])))) { e[r] = hi; eidx[r] = i0 + 1; }
           }
@@ -420,7 +522,7 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
     }
 
     // ---- guard: a runner-up chunk inside the search's error window => the whole tile, exactly, for that row ----
-    if (!MERGED || vmask != 0ull) {
+    if (!MERGED) {
       #pragma unroll
       for (int r = 0; r < R; ++r) {
         float ax, ay, az, dummy;
@@ -434,14 +536,14 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
           float m;
           int mi = 0;
           const int* tile_perm = nullptr;
-          if (MERGED && !MATRIX) tile_perm = (dir == 0 ? p.permY + (long long)cj * p.strideY : p.permX + (long long)ci * p.strideX) + te * TILE;
+          if (MERGED && !MATRIX) tile_perm = (dir == 0 ? p.permY + (long long)cj * p.strideY : p.permX + (long long)ci * p.strideX) + te * TL;
           warp_tile_exact_min<!MATRIX>(tp, nch * PR, __shfl_sync(0xffffffffu, ax, src), __shfl_sync(0xffffffffu, ay, src),
                                        __shfl_sync(0xffffffffu, az, src), lane, tile_perm, m, mi);
           if (lane == src) {
             if (MATRIX) {
               eb[r] = fminf(eb[r], m);
             } else if (mi != 0x7fffffff) {
-              mi += te * TILE;
+              mi += te * TL;
               if (m < eb[r] || (m == eb[r] && before(dir, mi, ei[r]))) { eb[r] = m; ei[r] = mi; }
             }
           }
@@ -449,6 +551,65 @@ __global__ void __launch_bounds__(NT, R >= 8 ? 512 / NT : (R == 4 ? 3 : 4)) nn_k
       }
     }
 
+    }
+
+    // ---- DEFERRED (merged clouds): after the last tile of a row block, the exact pass on each row's winning chunk
+    //      and the guard over the whole cloud, both straight from global memory (L2): once per row block instead
+    //      of once per tile, which is what lets pruned launches use small tiles and small CTAs ----
+    if (MERGED && t == nt - 1 && rb * RB + (tid >> 5) * (32 * R) < rowcount) {      // warp-uniform
+      const float4* const cand = dir == 0 ? sy : sx;
+      const int* const cperm = MATRIX ? nullptr : (dir == 0 ? p.permY + (long long)cj * p.strideY : p.permX + (long long)ci * p.strideX);
+      const float4* const cboxes = !prune ? nullptr
+          : (dir == 0 ? bxY + (long long)cj * (p.paddedY / CHUNK * 2) : bxX + (long long)ci * (p.paddedX / CHUNK * 2));
+      #pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float ax, ay, az, dummy;
+        unpack2(nax[r], ax, dummy); unpack2(nay[r], ay, dummy); unpack2(naz[r], az, dummy);
+        ax *= -0.5f; ay *= -0.5f; az *= -0.5f;
+        const bool live = K_ROW(r) < rowcount;
+        float e = __int_as_float(0x7f800000);
+        int eidx = 0x7fffffff;
+        if (live && cur[r] < __int_as_float(0x7f800000)) {
+          const f32x2 ax2 = pack2(ax, ax), ay2 = pack2(ay, ay), az2 = pack2(az, az);
+          const float4* cp = cand + (long long)cid[r] * CHUNK;
+          #pragma unroll 4
+          for (int k = 0; k < CHUNK / 2; ++k) {
+            const float4 q0 = cp[2 * k], q1 = cp[2 * k + 1];
+            const f32x2 dx = sub2(pack2(q0.x, q0.y), ax2);
+            const f32x2 dy = sub2(pack2(q0.z, q0.w), ay2);
+            const f32x2 dz = sub2(pack2(q1.x, q1.y), az2);
+            float lo, hi;
+            unpack2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lo, hi);
+            if (MATRIX) {
+              e = min3(e, lo, hi);
+            } else {
+              const int i0 = cid[r] * CHUNK + 2 * k;
+              if (lo < e || (lo == e && eidx != 0x7fffffff && cperm[i0] < cperm[eidx])) { e = lo; eidx = i0; }
+              if (hi < e || (hi == e && eidx != 0x7fffffff && cperm[i0 + 1] < cperm[eidx])) { e = hi; eidx = i0 + 1; }
+            }
+          }
+        }
+        eb[r] = e;
+        ei[r] = eidx;
+        const bool near_tie = live && sec[r] <= cur[r] + search_window(ax, ay, az, cur[r]);
+        unsigned flagged = __ballot_sync(0xffffffffu, near_tie);
+        while (flagged) {                         // warp-uniform
+          const int src = __ffs(flagged) - 1;
+          flagged &= flagged - 1;
+          float m;
+          int mi = 0x7fffffff;
+          warp_cloud_exact_min<!MATRIX>(cand, scanpadded / CHUNK, cboxes, __shfl_sync(0xffffffffu, e, src),
+                                        __shfl_sync(0xffffffffu, ax, src), __shfl_sync(0xffffffffu, ay, src),
+                                        __shfl_sync(0xffffffffu, az, src), lane, cperm, m, mi);
+          if (lane == src) {
+            if (MATRIX) {
+              eb[r] = fminf(eb[r], m);
+            } else if (mi != 0x7fffffff && (m < eb[r] || (m == eb[r] && (ei[r] == 0x7fffffff || cperm[mi] < cperm[ei[r]])))) {
+              eb[r] = m; ei[r] = mi;
+            }
+          }
+        }
+      }
     }
 
     // ---- end of a (direction, row block): emit ----
@@ -801,16 +962,16 @@ static int pick_r(int maxcount) {
   return 1;
 }
 
-template <int R, bool MATRIX, bool MERGED, int NT = TPB>
+template <int R, bool MATRIX, bool MERGED, int NT = TPB, int TL = TILE>
 static int launch_nn(const Params& p, dim3 grid, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};   // per instantiation and device: the attribute is per context
   const int dev = current_device();
   if (!configured[dev]) {
-    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX, MERGED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DUSTY_CUDA(cudaFuncSetAttribute(nn_kernel<R, MATRIX, MERGED, NT, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TL * 16));
     configured[dev] = true;
   }
-  const int tile_pts = (R >= 8 && NT == TPB) ? TILE : std::min(TILE, std::max(p.paddedX, p.paddedY));
-  nn_kernel<R, MATRIX, MERGED, NT><<<grid, NT, 2 * (size_t)tile_pts * 16, st>>>(p);
+  const int tile_pts = (R >= 8 && NT == TPB) ? TL : std::min(TL, std::max(p.paddedX, p.paddedY));
+  nn_kernel<R, MATRIX, MERGED, NT, TL><<<grid, NT, 2 * (size_t)tile_pts * 16, st>>>(p);
   DUSTY_AFTER_LAUNCH("chamfer nn_kernel");
   return 0;
 }
@@ -889,6 +1050,11 @@ static int run_prep_sort(const float* xyz, long long clouds, int count, float4* 
 using namespace dusty;
 using namespace dusty::chamfer;
 
+// Measurement only (bench.py, roofline of the pruned workloads): when switched on, the merged-origin kernels add the
+// number of (row, candidate) pairs they really evaluate to a device counter.
+static unsigned long long* g_visited_counter = nullptr;
+
+
 // Un-sampled clouds in the batch front end (compute_cd on (B, H*W, 3) pairs, reference evaluate_reconstruction.py:
 // 124-131): the same treatment as the matrix front end -- zero points merged into one candidate, kept points
 // Morton-sorted with a box per chunk, chunks pruned by box distance -- plus the maps back to the original order.
@@ -956,9 +1122,11 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
     p.strideX = p.paddedX; p.strideY = p.paddedY;
     p.dist1 = X.dist; p.dist2 = Y.dist; p.idx1 = X.idx; p.idx2 = Y.idx;
     p.metaX = X.meta; p.metaY = Y.meta; p.boxX = X.boxes; p.boxY = Y.boxes; p.permX = X.perm; p.permY = Y.perm;
+    p.visited = g_visited_counter;
     constexpr int R = 4;          // 128-row warps: the row boxes the pruning test uses stay tight (see dusty_chamfer_matrix)
     const int big = n > m ? n : m;
-    if (int rc = launch_nn<R, false, true>(p, dim3((big + TPB * R - 1) / (TPB * R), b, 2), st)) return rc;
+    constexpr int NTB = 64;       // two warps per CTA, 512-candidate tiles: see nn_kernel
+    if (int rc = launch_nn<R, false, true, NTB, 512>(p, dim3((big + NTB * R - 1) / (NTB * R), b, 2), st)) return rc;
     unsort_kernel<<<(unsigned)(((long long)b * n + 255) / 256), 256, 0, st>>>(X.dist, X.idx, X.inv, b, n, p.strideX, dist1, idx1);
     DUSTY_AFTER_LAUNCH("chamfer unsort_kernel");
     unsort_kernel<<<(unsigned)(((long long)b * m + 255) / 256), 256, 0, st>>>(Y.dist, Y.idx, Y.inv, b, m, p.strideY, dist2, idx2);
@@ -1093,10 +1261,19 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
   p.symmetric = symmetric; p.mirror = mirror; p.compact_rows = compact_rows;
   p.M = M; p.ldm = ldm;
   p.keys = fk.keys; p.n_total = fk.n_total; p.n_ref = fk.n_ref; p.offX = fk.off_a; p.offY = fk.off_b;
+  p.visited = g_visited_counter;
   const dim3 grid(nb, rows, 1);
   if (merge) {
     p.metaX = ma; p.metaY = mb;
     if (sorted) { p.boxX = ba; p.boxY = bb; }
+    static const bool narrow = [] { const char* e = getenv("DUSTY_CHAMFER_NARROW"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (sorted && merged_r == 4 && narrow) {
+      // Measured on 100 vs 100 un-sampled clouds, entries/s per GPU. Round 1 layout (256 threads, 2048-candidate tiles, exact
+      // pass per tile) 58.6 k; exact pass deferred to the end of a row block 62.8 k; + two warps per CTA with 512-candidate
+      // tiles 69.5 k; + the per-row second pruning level 92.3 k (R = 8 with 32 or 64 threads 91.2 k, 128 threads with
+      // 1024-candidate tiles 93.0 k, R = 2 72.5 k: a plateau).
+      return launch_nn<4, true, true, 64, 512>(p, grid, st);
+    }
     return dispatch_nn<true, true>(merged_r, p, grid, st);
   }
   return dispatch_matrix(pa > pb ? pa : pb, p, grid, st);
@@ -1128,4 +1305,22 @@ extern "C" int dusty_chamfer_matrix_fused(const float* A, int na, int pa, const 
   fk.keys = reinterpret_cast<unsigned long long*>(keys);
   fk.n_total = n_total; fk.n_ref = n_ref; fk.off_a = stacked_offset_a; fk.off_b = stacked_offset_b;
   return matrix_impl(A, na, pa, B, nb, pb, row_begin, row_end, row_stride, flags, M, ldm, fk, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dusty_chamfer_count_pairs(int enable, uint64_t* pairs_out) {
+  if (pairs_out) {
+    *pairs_out = 0;
+    if (g_visited_counter) {
+      DUSTY_CUDA(cudaDeviceSynchronize());
+      unsigned long long v = 0;
+      DUSTY_CUDA(cudaMemcpy(&v, g_visited_counter, sizeof(v), cudaMemcpyDeviceToHost));
+      *pairs_out = v;
+    }
+  }
+  if (enable && !g_visited_counter) {
+    DUSTY_CUDA(cudaMalloc(&g_visited_counter, sizeof(unsigned long long)));
+  }
+  if (g_visited_counter) DUSTY_CUDA(cudaMemset(g_visited_counter, 0, sizeof(unsigned long long)));
+  if (!enable && g_visited_counter) { DUSTY_CUDA(cudaFree(g_visited_counter)); g_visited_counter = nullptr; }
+  return 0;
 }

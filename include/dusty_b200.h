@@ -333,6 +333,13 @@ DUSTY_API int dusty_scan_preprocess(const dusty_scan_params* p, const float* sca
  * -------------------------------------------------------------------------------------------- */
 DUSTY_API int dusty_probe_fp32_peak(int iters, float* sink, double* flops_out, void* stream);
 
+/* Measurement helper (bench.py only): the merged-origin / pruned Chamfer kernels skip candidate chunks by an exact
+ * box bound, so the number of (row, candidate) pairs they evaluate is data dependent. enable != 0 switches a device
+ * counter on (per process and current device; the kernels then add to it with one atomic per warp and tile),
+ * enable == 0 switches it off; either way *pairs_out (may be NULL) receives the count accumulated since the last
+ * call and the counter restarts at zero. Not for timed runs: the call synchronises the device. */
+DUSTY_API int dusty_chamfer_count_pairs(int enable, uint64_t* pairs_out);
+
 #ifdef __cplusplus
 }
 #endif
