@@ -1060,8 +1060,9 @@ static unsigned long long* g_visited_counter = nullptr;
 // Morton-sorted with a box per chunk, chunks pruned by box distance -- plus the maps back to the original order.
 static bool forward_takes_sorted_path(int n, int m) {
   static const bool enabled = [] { const char* e = getenv("DUSTY_CHAMFER_BATCH_SORT"); return !(e && e[0] == '0'); }();
+  static const int above = [] { const char* e = getenv("DUSTY_CHAMFER_BATCH_SORT_ABOVE"); return e ? atoi(e) : 4096; }();
   const int big = n > m ? n : m;
-  return enabled && big > 4096 && big <= SORT_CAP;
+  return enabled && big > above && big <= SORT_CAP;
 }
 
 namespace {

@@ -175,12 +175,17 @@ def test_matrix_merged_origin_points(shape):
         assert np.array_equal(sub[1::2], merged[1::2])
 
 
-def test_matrix_merge_is_the_default_for_unsampled_clouds():
+def test_matrix_sorted_search_is_the_default_above_1024_points():
     from dusty_gan_b200.utils.metrics import cov_mmd_1nna as M
-    a = lidar_like_clouds(2, M.MERGE_ORIGIN_ABOVE + 4, 611, dropped=0.5)
+    assert M.MERGE_ORIGIN_ABOVE == 1024
+    a = lidar_like_clouds(2, 4100, 611, dropped=0.5)
     assert np.array_equal(matrix(a), matrix(a, merge_origin=True))
-    s = sampled_clouds(2, 2048, 612)
-    assert np.array_equal(matrix(s), matrix(s, merge_origin=False))
+    s = sampled_clouds(3, 2048, 612)                        # the evaluation's own shape: sorted + pruned too
+    S1, S0 = matrix(s), matrix(s, merge_origin=False)
+    assert np.array_equal(S1, matrix(s, merge_origin=True))
+    assert np.all(np.abs(S1 - S0) <= ULP * S0)              # same distances, the two means summed in another order
+    small = sampled_clouds(3, 1024, 613)                    # at and below 1024 points: the brute-force kernel
+    assert np.array_equal(matrix(small), matrix(small, merge_origin=False))
 
 
 def test_matrix_golden_reference_driver(golden):
