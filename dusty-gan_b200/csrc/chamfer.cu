@@ -1361,7 +1361,10 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
     if (sorted) { p.boxX = ba; p.boxY = bb; }
     if (pair) {
       static const int pair_r = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
-      return pair_r == 1 ? launch_pair<1>(p, grid, st) : pair_r == 4 ? launch_pair<4>(p, grid, st) : launch_pair<2>(p, grid, st);
+      static const int pair_sub = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_SUB"); const int v = e ? atoi(e) : 8; return v == 16 || v == 32 ? v : 8; }();
+      if (pair_sub == 16) return pair_r == 4 ? launch_pair<4, 16>(p, grid, st) : launch_pair<2, 16>(p, grid, st);
+      if (pair_sub == 32) return launch_pair<2, 32>(p, grid, st);
+      return pair_r == 1 ? launch_pair<1, 8>(p, grid, st) : pair_r == 4 ? launch_pair<4, 8>(p, grid, st) : launch_pair<2, 8>(p, grid, st);
     }
     static const bool narrow = [] { const char* e = getenv("DUSTY_CHAMFER_NARROW"); return !(e && e[0] == '0'); }();   // A/B switch
     if (sorted && merged_r == 4 && narrow) {

@@ -21,7 +21,7 @@
 constexpr int PAIR_CAP = 2048;
 constexpr int PAIR_NW = 8;                 // warps per CTA
 
-template <int R>
+template <int R, int SUB>
 __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -128,30 +128,38 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
       }
       if (!__any_sync(0xffffffffu, need)) continue;
       ++nvis;
+      // search, tracked per SUB-candidate window: the exact pass re-reads only the winning window of each row (every
+      // lane another one: with whole chunks those loads, not the scan's broadcasts, saturated shared memory)
       const float4* cp = cand + c * CHUNK;
-      float cm[R];
       #pragma unroll
-      for (int k = 0; k < CHUNK / 2; ++k) {
-        const float4 q0 = cp[2 * k], q1 = cp[2 * k + 1];
-        const f32x2 bx = pack2(q0.x, q0.y), by = pack2(q0.z, q0.w);
-        const f32x2 bz = pack2(q1.x, q1.y), bn = pack2(q1.z, q1.w);
+      for (int w = 0; w < CHUNK / SUB; ++w) {
+        float cm[R];
+        #pragma unroll
+        for (int k = w * (SUB / 2); k < (w + 1) * (SUB / 2); ++k) {
+          const float4 q0 = cp[2 * k], q1 = cp[2 * k + 1];
+          const f32x2 bx = pack2(q0.x, q0.y), by = pack2(q0.z, q0.w);
+          const f32x2 bz = pack2(q1.x, q1.y), bn = pack2(q1.z, q1.w);
+          #pragma unroll
+          for (int r = 0; r < R; ++r) {
+            f32x2 s = fma2(naz[r], bz, bn);
+            s = fma2(nay[r], by, s);
+            s = fma2(nax[r], bx, s);
+            float lo, hi;
+            unpack2(s, lo, hi);
+            cm[r] = (k == w * (SUB / 2)) ? fminf(lo, hi) : min3(cm[r], lo, hi);
+          }
+        }
         #pragma unroll
         for (int r = 0; r < R; ++r) {
-          f32x2 s = fma2(naz[r], bz, bn);
-          s = fma2(nay[r], by, s);
-          s = fma2(nax[r], bx, s);
-          float lo, hi;
-          unpack2(s, lo, hi);
-          cm[r] = (k == 0) ? fminf(lo, hi) : min3(cm[r], lo, hi);
+          const bool better = cm[r] < cur[r];
+          sec[r] = fminf(sec[r], fmaxf(cur[r], cm[r]));      // runner-up: the smallest minimum of any other window
+          cur[r] = fminf(cur[r], cm[r]);
+          cid[r] = better ? c * (CHUNK / SUB) + w : cid[r];
         }
       }
       float m = 0.0f;
       #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const bool better = cm[r] < cur[r];
-        sec[r] = fminf(sec[r], better ? cur[r] : cm[r]);
-        cur[r] = better ? cm[r] : cur[r];
-        cid[r] = better ? c : cid[r];
         // upper bound of the row's final exact minimum (see nn_kernel, DEFERRED): dest + 64 u (|a|^2 + dest)
         if (ubr[r] >= 0.0f) {
           const float dest = fmaxf(cur[r] + an[r], 0.0f);
@@ -175,10 +183,10 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
       float e = inf;
       if (live && cur[r] < inf) {
         const f32x2 ax2 = pack2(ax, ax), ay2 = pack2(ay, ay), az2 = pack2(az, az);
-        const float4* cp = cand + cid[r] * CHUNK;
-        #pragma unroll 4
-        for (int k = 0; k < CHUNK / 2; ++k) {
-          const int kk = (k + lane) & (CHUNK / 2 - 1);      // lanes start on different banks
+        const float4* cp = cand + cid[r] * SUB;
+        #pragma unroll
+        for (int k = 0; k < SUB / 2; ++k) {
+          const int kk = (k + lane) & (SUB / 2 - 1);      // lanes start on different banks
           const float4 q0 = cp[2 * kk], q1 = cp[2 * kk + 1];
           const f32x2 dx = sub2(pack2(q0.x, q0.y), ax2);
           const f32x2 dy = sub2(pack2(q0.z, q0.w), ay2);
@@ -230,17 +238,17 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
   }
 }
 
-template <int R>
+template <int R, int SUB>
 static int launch_pair(const Params& p, dim3 grid, cudaStream_t st) {
   const size_t smem = (size_t)(p.paddedX + p.paddedY) * 16 + (size_t)(p.paddedX / CHUNK + p.paddedY / CHUNK) * 32;
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    DUSTY_CUDA(cudaFuncSetAttribute(nn_pair_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DUSTY_CUDA(cudaFuncSetAttribute(nn_pair_kernel<R, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     2 * PAIR_CAP * 16 + 2 * (PAIR_CAP / CHUNK) * 32));
     configured[dev] = true;
   }
-  nn_pair_kernel<R><<<grid, PAIR_NW * 32, smem, st>>>(p);
+  nn_pair_kernel<R, SUB><<<grid, PAIR_NW * 32, smem, st>>>(p);
   DUSTY_AFTER_LAUNCH("chamfer nn_pair_kernel");
   return 0;
 }
