@@ -608,7 +608,7 @@ def main():
     alg_flops = entries * flops_per_entry / world                           # per launch, this GPU's share
     exe_entries = (2 * N) * (2 * N + 1) / 2                                 # stacked upper triangle incl. diagonal
     exe_flops = exe_entries * flops_per_entry / world
-    # Clouds above 1024 points take the sorted search, which skips candidate chunks by an exact box bound: the pairs it
+    # Clouds above 256 points take the sorted search, which skips candidate chunks by an exact box bound: the pairs it
     # really evaluates are data dependent, so the kernel counts them in one extra, untimed evaluation (6 flop each).
     kept = torch.cat([(c != 0).any(-1).sum(1) + ((c == 0).all(-1).any(1)).long() for c in (ref, gen)]).double()
     kept_pairs = float((kept.sum() ** 2 + (kept ** 2).sum()) / 2) * 2 / world       # both directions, this rank's share
@@ -644,14 +644,16 @@ def main():
     exe_rate = exe_flops / (kern_ms * 1e-3) / 1e12
     alg_rate = alg_flops / (kern_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "fp32_ffma", "kernel": "dusty::chamfer::nn_kernel<4,1,1,64,512> (sorted + pruned)" if pruned else "dusty::chamfer::nn_kernel<8,1,0,256>",
+        "bound": "fp32_ffma",
+        "kernel": ("dusty::chamfer::nn_pair_kernel<2,8> (k-d ordered clouds resident in shared memory, best-first pruned walk)" if pruned and P <= 2048
+                   else "dusty::chamfer::nn_kernel<4,1,1,64,512> (sorted + pruned)" if pruned else "dusty::chamfer::nn_kernel<8,1,0,256>"),
         "achieved": exe_rate, "peak": peak_nominal, "unit": "TFLOP/s",
         "frac": exe_rate / peak_nominal, "achieved_algorithmic": alg_rate, "frac_algorithmic": alg_rate / peak_nominal,
         "peak_source": f"nominal 148x128x2x{sm_max_mhz:.0f} MHz",
         "peak_probe_ffma_only": peak_probe, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step,
         "flops_per_entry": flops_per_entry, "entries_per_launch_executed": exe_entries / world,
         "entries_per_launch_algorithmic": entries / world, "pruned_search": merged, "brute_force_kernel_same_run": dense,
-        "traffic": ncu_traffic("chamfer_nn_kernel_pruned_n1000" if pruned else "chamfer_nn_kernel_n1000")
+        "traffic": ncu_traffic("chamfer_nn_pair_kernel_n1000" if pruned else "chamfer_nn_kernel_n1000")
         if (world == 1 and args.workload == "cfg2" and N == N_CLOUDS) else None,
         "note": "frac = flops EXECUTED (pairs the pruned search evaluated, kernel counter, x 6) / peak; frac_algorithmic = 3 N^2 entries x "
                 "12 P^2 (the reference's work; > 1: most pairs are skipped, exactly)"}

@@ -876,12 +876,12 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
     keys[i] = key;
   }
   // level 0 packs the kept points to the front (its keys carry the global box: one segment)
-  for (int seglen = n2; seglen >= 2 * CHUNK; seglen >>= 1) {
+  for (int seglen = n2; seglen >= 2 * CHUNK || seglen == n2; seglen >>= 1) {      // tiny clouds: one level packs them
     const int nseg = n2 / seglen;
     for (int sgi = tid; sgi < 3 * nseg; sgi += SORT_TPB) { seglo[sgi] = 0xffffffffu; seghi[sgi] = 0u; }
     __syncthreads();
     for (int base = warp * 32; base < n2; base += SORT_TPB) {          // 32 consecutive positions: one segment
-      const unsigned key = keys[base + lane];
+      const unsigned key = base + lane < n2 ? keys[base + lane] : 0xffffffffu;
       float v[3] = {inf, inf, inf}, w[3] = {-inf, -inf, -inf};
       if (key != 0xffffffffu) {
         const int i = (int)(key & 0x7fffu);
@@ -1320,7 +1320,9 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
   // kernel prunes chunks by box distance (DUSTY_CHAMFER_PRUNE=0 keeps the plain merged scan for A/B runs)
   static const bool prune_enabled = [] { const char* e = getenv("DUSTY_CHAMFER_PRUNE"); return !(e && e[0] == '0'); }();
   int merged_r = pick_r(pa > pb ? pa : pb);
-  const bool sorted = merge && prune_enabled && pa <= SORT_CAP && pb <= SORT_CAP && merged_r == 8;
+  static const bool pair_enabled = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR"); return !(e && e[0] == '0'); }();
+  const bool pair = merge && prune_enabled && pair_enabled && pa <= PAIR_CAP && pb <= PAIR_CAP;
+  const bool sorted = merge && prune_enabled && pa <= SORT_CAP && pb <= SORT_CAP && (merged_r == 8 || pair);
   if (sorted) {
     // Pruning works per warp, and a warp owns 32 R consecutive sorted rows: fewer rows per thread give tighter row
     // boxes (more chunks skipped) against fewer FFMA2 per LDS. Measured on the bench's un-sampled clouds, entries/s
@@ -1329,8 +1331,6 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
     if (const char* e = getenv("DUSTY_CHAMFER_MERGED_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) merged_r = v; }
   }
   // clouds that fit shared memory twice over (the evaluation's 2048 FPS samples): k-d order + the resident-pair kernel
-  static const bool pair_enabled = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR"); return !(e && e[0] == '0'); }();
-  const bool pair = sorted && pair_enabled && pa <= PAIR_CAP && pb <= PAIR_CAP;
   if (!prepared) {
     if (sorted) {
       if (int rc = run_prep_sort(A, na, pa, sa, ma, ba, st, nullptr, nullptr, pair)) return rc;

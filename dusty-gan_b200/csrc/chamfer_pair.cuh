@@ -25,7 +25,9 @@ template <int R, int SUB>
 __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
-  __shared__ double red[PAIR_NW];
+  // per-task sums: a task's sum is formed in a fixed order inside its warp and the tasks are added in task order, so the
+  // entry does not depend on which warp happened to take which task
+  __shared__ double tsum[2 * (PAIR_CAP / (32 * R))];
   __shared__ int next_task;
   const int tid = threadIdx.x, lane = tid & 31;
 
@@ -56,7 +58,6 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
   constexpr int GR = 32 * R;                     // rows per group
   const int ngX = (mx.x + GR - 1) / GR, ngY = (my.x + GR - 1) / GR;
   const float inf = __int_as_float(0x7f800000);
-  double dsum0 = 0.0, dsum1 = 0.0;
 
   for (;;) {
     int task = 0;
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
     if (p.visited != nullptr && lane == 0)
       atomicAdd(p.visited, (unsigned long long)nvis * CHUNK * (unsigned long long)min(GR, rowcount - g * GR));
 
-    // ---- exact pass on each row's winning chunk, guard over the whole candidate cloud ----
+    // ---- exact pass on each row's winning window, guard over the whole candidate cloud ----
+    double dsum = 0.0;
     #pragma unroll
     for (int r = 0; r < R; ++r) {
       float ax, ay, az, dummy;
@@ -207,16 +209,18 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
                                     __shfl_sync(0xffffffffu, ay, src), __shfl_sync(0xffffffffu, az, src), lane, nullptr, m, mi);
         if (lane == src) e = fminf(e, m);
       }
-      if (live) {
-        const double w = row == rowcount - 1 ? (double)(dir ? my.y : mx.y) : 1.0;
-        if (dir) dsum1 += w * (double)e; else dsum0 += w * (double)e;
-      }
+      if (live) dsum += (row == rowcount - 1 ? (double)(dir ? my.y : mx.y) : 1.0) * (double)e;
     }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+    if (lane == 0) tsum[task] = dsum;
   }
 
-  const double S0 = block_sum<PAIR_NW * 32>(dsum0, red);
-  const double S1 = block_sum<PAIR_NW * 32>(dsum1, red);
+  __syncthreads();
   if (tid == 0) {
+    double S0 = 0.0, S1 = 0.0;
+    for (int t = 0; t < ngX; ++t) S0 += tsum[t];
+    for (int t = ngX; t < ngX + ngY; ++t) S1 += tsum[t];
     const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
     if (p.M) {
       p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;

@@ -52,7 +52,7 @@ FUSED_EPILOGUE = True
 # same path (and every row shard of a matrix the same one). Smaller clouds keep the brute-force kernel: its register
 # tile, not pruning, is what pays there. Set it to a huge value to force the brute-force kernel (bench.py does, for
 # the roofline of that kernel).
-MERGE_ORIGIN_ABOVE = 1024
+MERGE_ORIGIN_ABOVE = 256
 
 
 def chamfer_matrix(pcs_1, pcs_2=None, rows=None, compact_rows=False, out=None, merge_origin=None, fused=None):

@@ -175,17 +175,52 @@ def test_matrix_merged_origin_points(shape):
         assert np.array_equal(sub[1::2], merged[1::2])
 
 
-def test_matrix_sorted_search_is_the_default_above_1024_points():
+def test_matrix_sorted_search_is_the_default_above_256_points():
     from dusty_gan_b200.utils.metrics import cov_mmd_1nna as M
-    assert M.MERGE_ORIGIN_ABOVE == 1024
+    assert M.MERGE_ORIGIN_ABOVE == 256
     a = lidar_like_clouds(2, 4100, 611, dropped=0.5)
     assert np.array_equal(matrix(a), matrix(a, merge_origin=True))
-    s = sampled_clouds(3, 2048, 612)                        # the evaluation's own shape: sorted + pruned too
+    s = sampled_clouds(3, 2048, 612)                        # the evaluation's own shape: k-d order + resident-pair kernel
     S1, S0 = matrix(s), matrix(s, merge_origin=False)
     assert np.array_equal(S1, matrix(s, merge_origin=True))
     assert np.all(np.abs(S1 - S0) <= ULP * S0)              # same distances, the two means summed in another order
-    small = sampled_clouds(3, 1024, 613)                    # at and below 1024 points: the brute-force kernel
+    small = sampled_clouds(3, 256, 613)                     # at and below 256 points: the brute-force kernel
     assert np.array_equal(matrix(small), matrix(small, merge_origin=False))
+
+
+@pytest.mark.parametrize("pa,pb,dropped", [(257, 300, 0.0), (512, 512, 0.0), (1000, 777, 0.3), (2047, 2048, 0.0),
+                                            (2048, 2048, 0.4), (2048, 65, 0.5), (33, 2048, 0.2), (2048, 2049, 0.0)])
+def test_matrix_resident_pair_kernel_against_oracle(pa, pb, dropped):
+    """Clouds of at most 2048 points with merged origins: k-d ordered by prep_sort_kernel<true>, searched by
+    nn_pair_kernel (both clouds in shared memory, best-first chunk walk). Every entry against the CUDA-rounding
+    oracle, for point counts that are not multiples of the 64-row groups or the 32-candidate chunks, clouds with
+    and without dropped (0,0,0) points, degenerate clouds, and 2049 points (one past the kernel's capacity: the
+    Morton-sorted tile kernel). Two runs are bit-identical although warps take their row groups dynamically."""
+    a = lidar_like_clouds(4, pa, 700 + pa, dropped=dropped); b = lidar_like_clouds(3, pb, 800 + pb, dropped=dropped)
+    b[1] = b[1][0]                                           # every point the same
+    if dropped:
+        a[1] = 0.0                                           # only origin points
+    M = matrix(a, b, merge_origin=True)
+    assert_entries_equal(M, native.pairwise_cd(a, b, rounding="cuda"))
+    assert np.array_equal(M, matrix(a, b, merge_origin=True))
+    if pa == pb:
+        S = matrix(a, merge_origin=True)
+        assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0)
+        assert_entries_equal(S, native.pairwise_cd(a, None, rounding="cuda"))
+        from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix
+        sub = chamfer_matrix(cuda(a), None, rows=(1, 4, 2), compact_rows=True, merge_origin=True).cpu().numpy()
+        assert np.array_equal(sub[0, 1:], S[1, 1:]) and np.array_equal(sub[1, 3:], S[3, 3:])
+
+
+def test_matrix_resident_pair_kernel_on_clustered_and_collinear_clouds():
+    """k-d splits on clouds whose boxes degenerate: all points on a line (two zero-extent axes), many duplicates (equal
+    sort keys broken by index), two far-apart clusters (empty space inside the top-level boxes)."""
+    rng = np.random.default_rng(9)
+    line = np.zeros((2, 1024, 3), np.float32); line[:, :, 0] = rng.uniform(-1, 1, (2, 1024))
+    dup = np.repeat(rng.uniform(-0.5, 0.5, (2, 16, 3)).astype(np.float32), 64, axis=1)
+    two = np.concatenate([rng.normal(0.8, 0.01, (2, 700, 3)), rng.normal(-0.8, 0.01, (2, 324, 3))], axis=1).astype(np.float32)
+    for a, b in ((line, dup), (dup, two), (two, line)):
+        assert_entries_equal(matrix(a, b, merge_origin=True), native.pairwise_cd(a, b, rounding="cuda"))
 
 
 def test_matrix_golden_reference_driver(golden):
