@@ -60,6 +60,7 @@ struct Params {
   // sorted position back to the original point index (the merged origin point maps to the first zero point)
   const int2* metaX; const int2* metaY;
   const float4* boxX; const float4* boxY;
+  const float4* bbX; const float4* bbY;      // boxes of the blocks of 32 chunks (k-d ordered clouds, nn_walk_kernel)
   const int* permX; const int* permY;
   unsigned long long* visited;   // measurement only (null: off): (row, candidate) pairs the pruned search really evaluated
   // fused MMD/COV/1-NNA epilogue (matrix front end; null: off). keys = 3 arrays of n_total packed
@@ -150,7 +151,7 @@ __device__ __forceinline__ void warp_cloud_exact_min(const float4* cloud, int nc
     if (boxes != nullptr) {
       const float4 bl = boxes[2 * ch], bh = boxes[2 * ch + 1];
       const float gx = max3(0.0f, bl.x - ax, ax - bh.x), gy = max3(0.0f, bl.y - ay, ay - bh.y), gz = max3(0.0f, bl.z - az, az - bh.z);
-      if (fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))) > thr) continue;      // cannot reach (or tie) thr
+      if (bl.w == 0.0f && fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy))) > thr) continue;      // cannot reach (or tie) thr; .w: holds the origin
     }
     const float4* cp = cloud + (long long)ch * CHUNK;
     #pragma unroll 4
@@ -754,6 +755,7 @@ __global__ void __launch_bounds__(256) prep_merge_kernel(const float* __restrict
 // exact, because every operation of the distance is monotone in |dx|,|dy|,|dz| and so is rounding.
 constexpr int SORT_CAP = 32768;
 constexpr int SORT_TPB = 1024;
+constexpr int WALK_BLOCKS = SORT_CAP / CHUNK / 32;      // blocks of 32 chunks per cloud (upper level of the best-first walk)
 
 __device__ __forceinline__ unsigned spread7(unsigned v) {          // abcdefg -> a0b0c0d0e0f0g
   v &= 0x7fu;
@@ -783,7 +785,8 @@ template <bool KD>
 __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __restrict__ xyz, int count, long long stride,
                                                              float4* __restrict__ out, int2* __restrict__ meta,
                                                              float4* __restrict__ boxes, int boxstride,
-                                                             int* __restrict__ perm_all, int* __restrict__ inv_all) {
+                                                             int* __restrict__ perm_all, int* __restrict__ inv_all,
+                                                             float4* __restrict__ block_boxes) {
   extern __shared__ unsigned keys[];            // n2 keys (next power of two >= count)
   __shared__ float red[SORT_TPB / 32][6];
   __shared__ int wsum[SORT_TPB / 32];
@@ -835,6 +838,9 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
     #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], red[w][a]); hi[a] = fmaxf(hi[a], red[w][3 + a]); }
   }
+  // k-d order: a lone (0,0,0) point is an ordinary point (FPS samples keep at most one); only two or more collapse
+  const bool single = KD && count - total == 1;
+  if (single) total = count;
   const float sxs = hi[0] > lo[0] ? 128.0f / (hi[0] - lo[0]) : 0.0f;
   const float sys = hi[1] > lo[1] ? 128.0f / (hi[1] - lo[1]) : 0.0f;
   const float szs = hi[2] > lo[2] ? 2.0f / (hi[2] - lo[2]) : 0.0f;
@@ -872,7 +878,7 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
   __shared__ unsigned seglo[KD ? 3 * KD_MAXSEG : 1], seghi[KD ? 3 * KD_MAXSEG : 1];
   for (int i = tid; i < n2; i += SORT_TPB) {
     unsigned key = 0xffffffffu;
-    if (i < count && (src[3 * i] != 0.0f || src[3 * i + 1] != 0.0f || src[3 * i + 2] != 0.0f)) key = (unsigned)i;
+    if (i < count && (single || src[3 * i] != 0.0f || src[3 * i + 1] != 0.0f || src[3 * i + 2] != 0.0f)) key = (unsigned)i;
     keys[i] = key;
   }
   // level 0 packs the kept points to the front (its keys carry the global box: one segment)
@@ -930,7 +936,7 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
   }
   }
 
-  if (inv != nullptr) {                         // zero points: all stand behind the one origin point
+  if (inv != nullptr && !single) {              // zero points: all stand behind the one origin point
     for (int i = tid; i < count; i += SORT_TPB) {
       if (src[3 * i] == 0.0f && src[3 * i + 1] == 0.0f && src[3 * i + 2] == 0.0f) { inv[i] = total; atomicMin(&first_zero, i); }
     }
@@ -957,7 +963,10 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
     }
     float* q = dst + (size_t)(pos >> 1) * 8 + (pos & 1);     // {x0,x1,y0,y1}{z0,z1,n0,n1}
     q[0] = x; q[2] = y; q[4] = z; q[6] = n;
-    const bool real = pos < kept;
+    // consumers that walk chunks by box bound (block_boxes != null): the merged origin point stays outside its chunk's
+    // box (it would stretch the last leaf's box to the sensor) and the chunk is flagged in .w: always visited
+    const bool sep = block_boxes != nullptr && zeros > 0;
+    const bool real = pos < (sep ? total : kept);
     float l0 = real ? x : inf, l1 = real ? y : inf, l2 = real ? z : inf;
     float h0 = real ? x : -inf, h1 = real ? y : -inf, h2 = real ? z : -inf;
     #pragma unroll
@@ -966,9 +975,30 @@ __global__ void __launch_bounds__(SORT_TPB, 1) prep_sort_kernel(const float* __r
       l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
       l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
     }
-    if (lane == 0) { bdst[2 * chunk] = make_float4(l0, l1, l2, 0.f); bdst[2 * chunk + 1] = make_float4(h0, h1, h2, 0.f); }
+    if (lane == 0) {
+      bdst[2 * chunk] = make_float4(l0, l1, l2, sep && chunk == padded / CHUNK - 1 ? 1.0f : 0.0f);
+      bdst[2 * chunk + 1] = make_float4(h0, h1, h2, 0.f);
+    }
   }
   if (tid == 0) meta[c] = make_int2(kept, zeros > 0 ? zeros : 1);
+  // ---- boxes of the blocks of 32 chunks (the upper level of nn_walk_kernel's best-first walk); empty: (+inf, -inf) ----
+  if (block_boxes != nullptr) {
+    __syncthreads();                            // this CTA's chunk boxes are visible
+    float4* const bb = block_boxes + c * (2 * WALK_BLOCKS);
+    const int nchunks = padded / CHUNK;
+    for (int b = warp; b < WALK_BLOCKS; b += SORT_TPB / 32) {
+      const int chunk = b * 32 + lane;
+      float4 bl = make_float4(inf, inf, inf, 0.f), bh = make_float4(-inf, -inf, -inf, 0.f);
+      if (chunk < nchunks) { bl = bdst[2 * chunk]; bh = bdst[2 * chunk + 1]; }
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        bl.x = fminf(bl.x, __shfl_xor_sync(0xffffffffu, bl.x, o)); bh.x = fmaxf(bh.x, __shfl_xor_sync(0xffffffffu, bh.x, o));
+        bl.y = fminf(bl.y, __shfl_xor_sync(0xffffffffu, bl.y, o)); bh.y = fmaxf(bh.y, __shfl_xor_sync(0xffffffffu, bh.y, o));
+        bl.z = fminf(bl.z, __shfl_xor_sync(0xffffffffu, bl.z, o)); bh.z = fmaxf(bh.z, __shfl_xor_sync(0xffffffffu, bh.z, o));
+      }
+      if (lane == 0) { bb[2 * b] = bl; bb[2 * b + 1] = bh; }
+    }
+  }
 }
 
 // Reference ChamferDistanceGradKernel (chamfer_distance.cu:148-190): after two memsets, every point adds
@@ -1093,7 +1123,12 @@ static int run_prep_merge(const float* xyz, long long clouds, int count, float4*
   return 0;
 }
 
-static size_t box_bytes(long long clouds, int count) { return align_up((size_t)clouds * (padded_of(count) / CHUNK) * 32, 256); }
+static size_t chunk_box_bytes(long long clouds, int count) { return align_up((size_t)clouds * (padded_of(count) / CHUNK) * 32, 256); }
+// chunk boxes, then the boxes of the blocks of 32 chunks
+static size_t box_bytes(long long clouds, int count) { return chunk_box_bytes(clouds, count) + align_up((size_t)clouds * 2 * WALK_BLOCKS * 16, 256); }
+static float4* block_boxes_of(float4* boxes, long long clouds, int count) {
+  return reinterpret_cast<float4*>(reinterpret_cast<char*>(boxes) + chunk_box_bytes(clouds, count));
+}
 
 // (clouds, count) results at sorted positions -> the original point order (batch front end on sorted clouds)
 __global__ void __launch_bounds__(256) unsort_kernel(const float* __restrict__ dist_sorted, const int* __restrict__ idx_sorted,
@@ -1109,7 +1144,7 @@ __global__ void __launch_bounds__(256) unsort_kernel(const float* __restrict__ d
 
 template <bool KD>
 static int launch_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st,
-                            int* perm, int* inv) {
+                            int* perm, int* inv, bool walkable) {
   int n2 = 1;
   while (n2 < count) n2 <<= 1;
   static bool configured[kMaxDevices] = {};
@@ -1119,19 +1154,22 @@ static int launch_prep_sort(const float* xyz, long long clouds, int count, float
     configured[dev] = true;
   }
   prep_sort_kernel<KD><<<(unsigned)clouds, SORT_TPB, (size_t)n2 * 4, st>>>(xyz, count, padded_of(count), out, meta, boxes,
-                                                                            padded_of(count) / CHUNK * 2, perm, inv);
+                                                                            padded_of(count) / CHUNK * 2, perm, inv,
+                                                                            walkable ? block_boxes_of(boxes, clouds, count) : nullptr);
   DUSTY_AFTER_LAUNCH(KD ? "chamfer prep_sort_kernel<kd>" : "chamfer prep_sort_kernel");
   return 0;
 }
 
 static int run_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st,
-                         int* perm = nullptr, int* inv = nullptr, bool kd = false) {
+                         int* perm = nullptr, int* inv = nullptr, bool walkable = false, bool kd = true) {
+  // walkable: for nn_pair_kernel / nn_walk_kernel (block boxes, origin kept out of its chunk's box); kd: k-d order (Morton otherwise)
   if (clouds == 0) return 0;
-  return kd ? launch_prep_sort<true>(xyz, clouds, count, out, meta, boxes, st, perm, inv)
-            : launch_prep_sort<false>(xyz, clouds, count, out, meta, boxes, st, perm, inv);
+  return walkable && kd ? launch_prep_sort<true>(xyz, clouds, count, out, meta, boxes, st, perm, inv, walkable)
+                        : launch_prep_sort<false>(xyz, clouds, count, out, meta, boxes, st, perm, inv, walkable);
 }
 
 #include "chamfer_pair.cuh"
+#include "chamfer_walk.cuh"
 
 }  // namespace chamfer
 }  // namespace dusty
@@ -1203,8 +1241,10 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
   if (forward_takes_sorted_path(n, m)) {
     SortedSide X, Y;
     Y.carve(X.carve(static_cast<char*>(workspace), b, n), b, m);
-    if (int rc = run_prep_sort(xyz1, b, n, X.scan, X.meta, X.boxes, st, X.perm, X.inv)) return rc;
-    if (int rc = run_prep_sort(xyz2, b, m, Y.scan, Y.meta, Y.boxes, st, Y.perm, Y.inv)) return rc;
+    static const bool walk = [] { const char* e = getenv("DUSTY_CHAMFER_WALK"); return !(e && e[0] == '0'); }();
+    static const bool kd = [] { const char* e = getenv("DUSTY_CHAMFER_BATCH_KD"); return !(e && e[0] == '0'); }();
+    if (int rc = run_prep_sort(xyz1, b, n, X.scan, X.meta, X.boxes, st, X.perm, X.inv, walk, kd)) return rc;
+    if (int rc = run_prep_sort(xyz2, b, m, Y.scan, Y.meta, Y.boxes, st, Y.perm, Y.inv, walk, kd)) return rc;
     Params p{};
     p.scanX = X.scan; p.scanY = Y.scan;
     p.countX = n; p.countY = m;
@@ -1216,6 +1256,11 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
     constexpr int R = 4;          // 128-row warps: the row boxes the pruning test uses stay tight (see dusty_chamfer_matrix)
     const int big = n > m ? n : m;
     constexpr int NTB = 64;       // two warps per CTA, 512-candidate tiles: see nn_kernel
+    if (walk) {
+      p.bbX = block_boxes_of(X.boxes, b, n); p.bbY = block_boxes_of(Y.boxes, b, m);
+      const int tasks = (n + 63) / 64 + (m + 63) / 64 + 2;      // 64-row groups of both directions (+ the merged origin rows)
+      if (int rc = launch_walk<2, 8, false>(p, dim3((tasks + WALK_TPC - 1) / WALK_TPC, b, 1), st)) return rc;
+    } else
     if (int rc = launch_nn<R, false, true, NTB, 512>(p, dim3((big + NTB * R - 1) / (NTB * R), b, 2), st)) return rc;
     unsort_kernel<<<(unsigned)(((long long)b * n + 255) / 256), 256, 0, st>>>(X.dist, X.idx, X.inv, b, n, p.strideX, dist1, idx1);
     DUSTY_AFTER_LAUNCH("chamfer unsort_kernel");
@@ -1331,10 +1376,14 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
     if (const char* e = getenv("DUSTY_CHAMFER_MERGED_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) merged_r = v; }
   }
   // clouds that fit shared memory twice over (the evaluation's 2048 FPS samples): k-d order + the resident-pair kernel
+  // larger sorted clouds: k-d order + the two-level best-first walk from global memory (DUSTY_CHAMFER_WALK=0: Morton
+  // order + the tile-streaming nn_kernel, kept for A/B runs)
+  static const bool walk_enabled = [] { const char* e = getenv("DUSTY_CHAMFER_WALK"); return !(e && e[0] == '0'); }();
+  const bool walk = sorted && !pair && walk_enabled;
   if (!prepared) {
     if (sorted) {
-      if (int rc = run_prep_sort(A, na, pa, sa, ma, ba, st, nullptr, nullptr, pair)) return rc;
-      if (!symmetric) if (int rc = run_prep_sort(B, nb, pb, sb, mb, bb, st, nullptr, nullptr, pair)) return rc;
+      if (int rc = run_prep_sort(A, na, pa, sa, ma, ba, st, nullptr, nullptr, pair || walk)) return rc;
+      if (!symmetric) if (int rc = run_prep_sort(B, nb, pb, sb, mb, bb, st, nullptr, nullptr, pair || walk)) return rc;
     } else if (merge) {
       if (int rc = run_prep_merge(A, na, pa, sa, ma, st)) return rc;
       if (!symmetric) if (int rc = run_prep_merge(B, nb, pb, sb, mb, st)) return rc;
@@ -1358,7 +1407,8 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
   const dim3 grid(nb, rows, 1);
   if (merge) {
     p.metaX = ma; p.metaY = mb;
-    if (sorted) { p.boxX = ba; p.boxY = bb; }
+    if (sorted) { p.boxX = ba; p.boxY = bb; p.bbX = block_boxes_of(ba, na, pa); p.bbY = symmetric ? p.bbX : block_boxes_of(bb, nb, pb); }
+    if (walk) return launch_walk<2, 8, true>(p, grid, st);
     if (pair) {
       static const int pair_r = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
       static const int pair_sub = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_SUB"); const int v = e ? atoi(e) : 8; return v == 16 || v == 32 ? v : 8; }();

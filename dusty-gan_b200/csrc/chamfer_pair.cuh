@@ -93,15 +93,22 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
         const float4 bl = rbox[2 * (g * R + r)], bh = rbox[2 * (g * R + r) + 1];
         gl0 = fminf(gl0, bl.x); gl1 = fminf(gl1, bl.y); gl2 = fminf(gl2, bl.z);
         gh0 = fmaxf(gh0, bh.x); gh1 = fmaxf(gh1, bh.y); gh2 = fmaxf(gh2, bh.z);
+        if (bl.w != 0.0f) {          // the chunk also holds the merged origin point, kept outside its box
+          gl0 = fminf(gl0, 0.0f); gl1 = fminf(gl1, 0.0f); gl2 = fminf(gl2, 0.0f);
+          gh0 = fmaxf(gh0, 0.0f); gh1 = fmaxf(gh1, 0.0f); gh2 = fmaxf(gh2, 0.0f);
+        }
       }
     }
     // ---- lower bound of every candidate chunk: key = (bound with its low 6 mantissa bits cleared) | chunk ----
+    const bool forced = cbox[2 * (nch - 1)].w != 0.0f;      // the last chunk holds the merged origin (outside its box): always visited
     unsigned key[2];
     #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c = h * 32 + lane;
       key[h] = 0xffffffffu;
-      if (c < nch) {
+      if (forced && c == nch - 1) {
+        key[h] = (unsigned)c;
+      } else if (c < nch) {
         const float4 bl = cbox[2 * c], bh = cbox[2 * c + 1];
         const float gx = max3(0.0f, bl.x - gh0, gl0 - bh.x), gy = max3(0.0f, bl.y - gh1, gl1 - bh.y), gz = max3(0.0f, bl.z - gh2, gl2 - bh.z);
         const float lb = fmaf(gz, gz, fmaf(gx, gx, __fmul_rn(gy, gy)));
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
       if (key[0] == kwin) key[0] = 0xffffffffu;
       if (key[1] == kwin) key[1] = 0xffffffffu;
       const float4 bl = cbox[2 * c], bh = cbox[2 * c + 1];
-      bool need = false;
+      bool need = forced && c == nch - 1;
       #pragma unroll
       for (int r = 0; r < R; ++r) {
         float ax, ay, az, dummy;
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
         #pragma unroll
         for (int r = 0; r < R; ++r) {
           const bool better = cm[r] < cur[r];
-          sec[r] = fminf(sec[r], fmaxf(cur[r], cm[r]));      // runner-up: the smallest minimum of any other window
+          sec[r] = fminf(sec[r], better ? cur[r] : cm[r]);      // runner-up: the smallest minimum of any other window (NaN: all padding)
           cur[r] = fminf(cur[r], cm[r]);
           cid[r] = better ? c * (CHUNK / SUB) + w : cid[r];
         }

@@ -197,7 +197,8 @@ def test_fused_evaluation_never_allocates_an_n_by_n_tensor():
     extra = torch.cuda.max_memory_allocated() - base
     clouds_bytes = 2 * N * P * 3 * 4
     scan_bytes = 2 * N * P * 16
-    assert extra <= clouds_bytes + scan_bytes + (8 << 20), extra        # stacked copy + scan-format copy + 8 MB; no 400 MB matrix
+    box_bytes = scan_bytes // 16 + 2 * N * 1024      # a box per 32 points + 32 block boxes per cloud
+    assert extra <= clouds_bytes + scan_bytes + box_bytes + (8 << 20), extra        # stacked copy + scan-format copy + boxes + 8 MB; no 400 MB matrix
     m.FUSED_EPILOGUE = False
     try:
         plain = m.compute_cov_mmd_1nna(gen, ref, 512, ("cd",), verbose=False)
