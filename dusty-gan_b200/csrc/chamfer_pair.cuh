@@ -18,6 +18,28 @@
 // distance: oracle property test tests/test_oracle_golden.py), hence the results are the brute-force kernel's bit for
 // bit. Measured on the bench's 2048-point FPS clouds the walk evaluates 11 % of the pairs (Morton order + tile-order
 // visits of nn_kernel<4,1,1,64,512>: 38 %).
+// One matrix entry from its two directed sums: M[i,j] (+ mirror) and the fused MMD/COV/1-NNA reductions (see nn_kernel).
+__device__ __forceinline__ void emit_entry(const Params& p, int ci, int cj, double S0, double S1) {
+  const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
+  if (p.M) {
+    p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
+    if (p.symmetric && p.mirror && ci != cj) p.M[(long long)cj * p.ldm + ci] = v;
+  }
+  if (p.keys) {
+    const int gi = p.offX + ci, gj = p.offY + cj;
+    if (gi != gj) {
+      const unsigned long long vb = (unsigned long long)__float_as_uint(v) << 32;
+      atomicMin(p.keys + gj, vb | (unsigned)gi);
+      atomicMin(p.keys + gi, vb | (unsigned)gj);
+      const int lo = min(gi, gj), hi = max(gi, gj);
+      if (lo < p.n_ref && hi >= p.n_ref) {
+        atomicMin(p.keys + p.n_total + hi, vb | (unsigned)lo);
+        atomicMin(p.keys + 2 * (long long)p.n_total + lo, vb | (unsigned)hi);
+      }
+    }
+  }
+}
+
 constexpr int PAIR_CAP = 2048;
 constexpr int PAIR_NW = 8;                 // warps per CTA
 
@@ -228,24 +250,7 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
     double S0 = 0.0, S1 = 0.0;
     for (int t = 0; t < ngX; ++t) S0 += tsum[t];
     for (int t = ngX; t < ngX + ngY; ++t) S1 += tsum[t];
-    const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
-    if (p.M) {
-      p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
-      if (p.symmetric && p.mirror && ci != cj) p.M[(long long)cj * p.ldm + ci] = v;
-    }
-    if (p.keys) {                    // fused MMD/COV/1-NNA reductions: see nn_kernel
-      const int gi = p.offX + ci, gj = p.offY + cj;
-      if (gi != gj) {
-        const unsigned long long vb = (unsigned long long)__float_as_uint(v) << 32;
-        atomicMin(p.keys + gj, vb | (unsigned)gi);
-        atomicMin(p.keys + gi, vb | (unsigned)gj);
-        const int lo = min(gi, gj), hi = max(gi, gj);
-        if (lo < p.n_ref && hi >= p.n_ref) {
-          atomicMin(p.keys + p.n_total + hi, vb | (unsigned)lo);
-          atomicMin(p.keys + 2 * (long long)p.n_total + lo, vb | (unsigned)hi);
-        }
-      }
-    }
+    emit_entry(p, ci, cj, S0, S1);
   }
 }
 

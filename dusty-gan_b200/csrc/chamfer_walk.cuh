@@ -242,24 +242,7 @@ __global__ void __launch_bounds__(WALK_NW * 32, 3) nn_walk_kernel(const Params p
       double S0 = 0.0, S1 = 0.0;
       for (int t = 0; t < ngX; ++t) S0 += tsum[t];
       for (int t = ngX; t < ngX + ngY; ++t) S1 += tsum[t];
-      const float v = (float)(S0 / (double)p.countX) + (float)(S1 / (double)p.countY);
-      if (p.M) {
-        p.M[(long long)(p.compact_rows ? (int)blockIdx.y : ci) * p.ldm + cj] = v;
-        if (p.symmetric && p.mirror && ci != cj) p.M[(long long)cj * p.ldm + ci] = v;
-      }
-      if (p.keys) {                    // fused MMD/COV/1-NNA reductions: see nn_kernel
-        const int gi = p.offX + ci, gj = p.offY + cj;
-        if (gi != gj) {
-          const unsigned long long vb = (unsigned long long)__float_as_uint(v) << 32;
-          atomicMin(p.keys + gj, vb | (unsigned)gi);
-          atomicMin(p.keys + gi, vb | (unsigned)gj);
-          const int lo = min(gi, gj), hi = max(gi, gj);
-          if (lo < p.n_ref && hi >= p.n_ref) {
-            atomicMin(p.keys + p.n_total + hi, vb | (unsigned)lo);
-            atomicMin(p.keys + 2 * (long long)p.n_total + lo, vb | (unsigned)hi);
-          }
-        }
-      }
+      emit_entry(p, ci, cj, S0, S1);
     }
   }
 }
