@@ -43,8 +43,8 @@ __device__ __forceinline__ void emit_entry(const Params& p, int ci, int cj, doub
 constexpr int PAIR_CAP = 2048;
 constexpr int PAIR_NW = 8;                 // warps per CTA
 
-template <int R, int SUB>
-__global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p) {
+template <int R, int SUB, int NW = PAIR_NW>
+__global__ void __launch_bounds__(NW * 32, 3) nn_pair_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
   // per-task sums: a task's sum is formed in a fixed order inside its warp and the tasks are added in task order, so the
@@ -254,17 +254,17 @@ __global__ void __launch_bounds__(PAIR_NW * 32, 3) nn_pair_kernel(const Params p
   }
 }
 
-template <int R, int SUB>
+template <int R, int SUB, int NW = PAIR_NW>
 static int launch_pair(const Params& p, dim3 grid, cudaStream_t st) {
   const size_t smem = (size_t)(p.paddedX + p.paddedY) * 16 + (size_t)(p.paddedX / CHUNK + p.paddedY / CHUNK) * 32;
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    DUSTY_CUDA(cudaFuncSetAttribute(nn_pair_kernel<R, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DUSTY_CUDA(cudaFuncSetAttribute(nn_pair_kernel<R, SUB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     2 * PAIR_CAP * 16 + 2 * (PAIR_CAP / CHUNK) * 32));
     configured[dev] = true;
   }
-  nn_pair_kernel<R, SUB><<<grid, PAIR_NW * 32, smem, st>>>(p);
+  nn_pair_kernel<R, SUB, NW><<<grid, NW * 32, smem, st>>>(p);
   DUSTY_AFTER_LAUNCH("chamfer nn_pair_kernel");
   return 0;
 }

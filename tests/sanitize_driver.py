@@ -73,5 +73,11 @@ many = torch.from_numpy(lidar_like_clouds(150, 1500, 8)).cuda()          # > 148
 downsample_point_clouds(many, 24)
 print(chamfer_matrix(u, merge_origin=True))
 print(chamfer_matrix(u, u[:2, :600].contiguous(), merge_origin=True))
+# round 2, second session: k-d ordered clouds (prep_sort_kernel<true>), the resident-pair kernel (dynamic task counter, TMA loads,
+# guard from shared memory on the adversarial cluster, ragged point counts with a merged origin) and the two-level walk kernel
+# in both front ends (matrix above 2048 points, batch on un-sampled clouds)
+print(chamfer_matrix(cube[:, :2000].contiguous()))
+print(chamfer_matrix(u[:, :1999].contiguous(), u[:2, :777].contiguous()))
+print(chamfer_matrix(cube, u[:, :2100].contiguous()))
 torch.cuda.synchronize()
 print("sanitize driver done")
