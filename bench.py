@@ -646,7 +646,8 @@ def main():
     roofline = {
         "bound": "fp32_ffma",
         "kernel": ("dusty::chamfer::nn_pair_kernel<2,8> (k-d ordered clouds resident in shared memory, best-first pruned walk)" if pruned and P <= 2048
-                   else "dusty::chamfer::nn_kernel<4,1,1,64,512> (sorted + pruned)" if pruned else "dusty::chamfer::nn_kernel<8,1,0,256>"),
+                   else "dusty::chamfer::nn_walk_kernel<2,8,1> (k-d ordered clouds, two-level best-first pruned walk from global memory)" if pruned
+                   else "dusty::chamfer::nn_kernel<8,1,0,256>"),
         "achieved": exe_rate, "peak": peak_nominal, "unit": "TFLOP/s",
         "frac": exe_rate / peak_nominal, "achieved_algorithmic": alg_rate, "frac_algorithmic": alg_rate / peak_nominal,
         "peak_source": f"nominal 148x128x2x{sm_max_mhz:.0f} MHz",

@@ -51,16 +51,23 @@ json.dump(kernels, open(os.path.join(ROOT, "profiles", f"ncu_{R}_metrics.json"),
 traffic = {}
 for d in kernels:
     name = d["Kernel Name"][0]
-    key = ("chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0" in name or "nn_kernel<8, 1>" in name
+    key = ("chamfer_nn_pair_kernel_n1000" if "nn_pair_kernel" in name
+           else "chamfer_nn_walk_kernel_batch_8x32768" if "nn_walk_kernel<2, 8, 0" in name
+           else "chamfer_nn_walk_kernel_24x32768" if "nn_walk_kernel" in name
+           else "chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0" in name or "nn_kernel<8, 1>" in name
            else "chamfer_nn_kernel_batch_sorted_8x32768" if "nn_kernel<4, 0, 1" in name
            else "chamfer_nn_kernel_merged_24x32768" if "nn_kernel" in name
            else "head_project_dusty1_b256_compact" if "head_project_image" in name
            else "head_project_dusty1_b256" if "head_project" in name
+           else "chamfer_prep_sort_kd_24x32768" if "prep_sort_kernel<1" in name
            else "chamfer_prep_sort_24x32768" if "prep_sort" in name
            else "scan_preprocess_256x64x2048" if "scan_preprocess" in name
            else "fps_multi_888clouds" if "fps_multi" in name else "fps_pruned_148clouds")
     traffic[key] = to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"])
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+old = json.load(open(path)) if os.path.exists(path) else {}
+old.update(traffic)            # keys captured in earlier rounds (other kernels, A/B paths) stay
+json.dump(old, open(path, "w"), indent=1)
 
 src = os.path.join(ROOT, "gpurun_out", f"launches_{R}.csv")
 rows = [r for r in csv.reader(open(src)) if len(r) > 10]
