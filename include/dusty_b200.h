@@ -126,10 +126,12 @@ DUSTY_API size_t dusty_chamfer_matrix_workspace_bytes(int na, int pa, int nb, in
  *                                the minima are unchanged (duplicate candidates never change a
  *                                minimum, identical rows share theirs) and the means still divide
  *                                by pa / pb, so M is the same matrix for a fraction of the work.
- *                                Clouds of at most 32768 points are also put in spatial (Morton) order
- *                                with a bounding box per 32 points, and the kernel skips candidate
- *                                chunks whose box is no closer to a warp's rows than their current
- *                                minima -- exact, the bound is evaluated in the kernel's own rounding. */
+ *                                Clouds of at most 32768 points are also put in spatial (k-d) order
+ *                                with a bounding box per 32 points, and the kernel walks candidate
+ *                                chunks best first by box distance, skipping every chunk whose box is
+ *                                no closer to a warp's rows than their current minima -- exact, the
+ *                                bound is evaluated in the kernel's own rounding. Clouds of at most 2048
+ *                                points are searched from shared memory (both clouds resident). */
 #define DUSTY_MATRIX_SYMMETRIC    1
 #define DUSTY_MATRIX_MIRROR       2
 #define DUSTY_MATRIX_COMPACT_ROWS 4
