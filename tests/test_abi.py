@@ -51,7 +51,7 @@ def test_workspace_queries_without_a_gpu():
     lib = _lib.load()
     assert lib.dusty_chamfer_forward_workspace_bytes(2, 2048, 2048) == 2 * 2 * 2048 * 16
     assert lib.dusty_chamfer_forward_workspace_bytes(0, 5, 5) == 0
-    assert lib.dusty_chamfer_matrix_workspace_bytes(10, 33, 0, 33) == 10 * 64 * 16 + 256 + 768      # scan copies + per-cloud meta + chunk boxes
+    assert lib.dusty_chamfer_matrix_workspace_bytes(10, 33, 0, 33) == 10 * 64 * 16 + 256 + 768 + 10 * 64 * 16      # scan copies + per-cloud meta + chunk boxes + block boxes (32 x 2 float4 per cloud)
     assert lib.dusty_fps_workspace_bytes(3, 1001, 16) >= 3 * 4 * 1004 * 4
     assert lib.dusty_head_project_workspace_bytes(256, 64, 512) >= 256 * 8 * 4
     assert lib.dusty_cov_mmd_1nna_workspace_bytes(1000, 1000) > 0
