@@ -1412,6 +1412,7 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
   if (merge) {
     p.metaX = ma; p.metaY = mb;
     if (sorted) { p.boxX = ba; p.boxY = bb; p.bbX = block_boxes_of(ba, na, pa); p.bbY = symmetric ? p.bbX : block_boxes_of(bb, nb, pb); }
+    // rows per lane, measured on 100 vs 100 un-sampled clouds: 1: 109.9 ms (1.7 % of the kept pairs visited), 2: 83.7 ms (2.3 %), 4: 85.9 ms (3.2 %)
     if (walk) return launch_walk<2, 8, true>(p, grid, st);
     if (pair) {
       static const int pair_r = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
