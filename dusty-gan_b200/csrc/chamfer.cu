@@ -1424,6 +1424,8 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
       static const int pair_r = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
       // warps per CTA, measured on the 1000 vs 1000 x 2048 evaluation: 4: 466 ms, 6: 435, 8: 418, 10: 416, 12: 415 -- a plateau:
       // the kernel is bound by issue slots and FFMA2/FMNMX3 dispatch, not by latency
+      static const bool pair_split = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_SPLIT"); return !(e && e[0] == '0'); }();
+      if (pair_split) return launch_pair_split(p, grid, st);
       static const int pair_sub = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_SUB"); const int v = e ? atoi(e) : 8; return v == 16 || v == 32 ? v : 8; }();
       if (pair_sub == 16) return pair_r == 4 ? launch_pair<4, 16>(p, grid, st) : launch_pair<2, 16>(p, grid, st);
       if (pair_sub == 32) return launch_pair<2, 32>(p, grid, st);
