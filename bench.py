@@ -645,7 +645,7 @@ def main():
     alg_rate = alg_flops / (kern_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp32_ffma",
-        "kernel": ("dusty::chamfer::nn_pair_kernel<2,8> (k-d ordered clouds resident in shared memory, best-first pruned walk)" if pruned and P <= 2048
+        "kernel": ("dusty::chamfer::nn_pair_split_kernel (k-d ordered clouds resident in shared memory, best-first pruned walk, 32-row groups)" if pruned and P <= 2048
                    else "dusty::chamfer::nn_walk_kernel<2,8,1> (k-d ordered clouds, two-level best-first pruned walk from global memory)" if pruned
                    else "dusty::chamfer::nn_kernel<8,1,0,256>"),
         "achieved": exe_rate, "peak": peak_nominal, "unit": "TFLOP/s",

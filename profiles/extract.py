@@ -51,7 +51,7 @@ json.dump(kernels, open(os.path.join(ROOT, "profiles", f"ncu_{R}_metrics.json"),
 traffic = {}
 for d in kernels:
     name = d["Kernel Name"][0]
-    key = ("chamfer_nn_pair_kernel_n1000" if "nn_pair_kernel" in name
+    key = ("chamfer_nn_pair_kernel_n1000" if "nn_pair" in name
            else "chamfer_nn_walk_kernel_batch_8x32768" if "nn_walk_kernel<2, 8, 0" in name
            else "chamfer_nn_walk_kernel_24x32768" if "nn_walk_kernel" in name
            else "chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0" in name or "nn_kernel<8, 1>" in name

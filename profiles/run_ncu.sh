@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 fi
 # 2. the dominant kernel (nn_pair_kernel since round 2b; nn_kernel with DUSTY_CHAMFER_PRUNE=0), full set, at the bench's own size
 if [[ $STEPS == *c* ]]; then
-ncu --set full --clock-control none --import-source on -k regex:"nn_pair_kernel|nn_kernel" -s 1 -c 1 -f -o gpurun_out/prof_chamfer_${R} \
+ncu --set full --clock-control none --import-source on -k regex:"nn_pair|nn_kernel" -s 1 -c 1 -f -o gpurun_out/prof_chamfer_${R} \
     python bench.py --steps 1 --warmup 1 --skip-extras > gpurun_out/prof_chamfer_${R}.log 2>&1
 fi
 # 3. head + projection, real-scan preprocess, FPS and the merged-origin Chamfer kernel (last launch of each)
