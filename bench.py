@@ -646,7 +646,7 @@ def main():
     roofline = {
         "bound": "fp32_ffma",
         "kernel": ("dusty::chamfer::nn_pair_split_kernel (k-d ordered clouds resident in shared memory, best-first pruned walk, 32-row groups)" if pruned and P <= 2048
-                   else "dusty::chamfer::nn_walk_kernel<2,8,1> (k-d ordered clouds, two-level best-first pruned walk from global memory)" if pruned
+                   else "dusty::chamfer::nn_walk_split_kernel<1> (k-d ordered clouds, two-level best-first pruned walk from global memory, 32-row groups)" if pruned
                    else "dusty::chamfer::nn_kernel<8,1,0,256>"),
         "achieved": exe_rate, "peak": peak_nominal, "unit": "TFLOP/s",
         "frac": exe_rate / peak_nominal, "achieved_algorithmic": alg_rate, "frac_algorithmic": alg_rate / peak_nominal,

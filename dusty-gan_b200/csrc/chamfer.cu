@@ -1251,7 +1251,8 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
     // Order of the batch front end's clouds: each is searched once, so the sort is most of the call. Measured, 8 / 32 / 128 pairs
     // of 32768-point scans: Morton + tile kernel 0.87 / 1.25 / 2.87 ms, Morton + walk 0.96 / 1.19 / 2.27 ms, k-d + walk 3.45 /
     // 3.52 / 4.12 ms (the k-d sort alone is 1.56 ms per launch: ten segmented sorts). The matrix front end, where a cloud is
-    // searched 2 N times, takes the k-d order. DUSTY_CHAMFER_BATCH_KD=1 for A/B runs.
+    // searched 2 N times, takes the k-d order. DUSTY_CHAMFER_BATCH_KD=1 for A/B runs. (With the split walk kernel -- 32-row groups,
+    // four times the CTAs -- Morton + walk is 0.78 / 1.04 / 2.02 ms.)
     static const bool kd = [] { const char* e = getenv("DUSTY_CHAMFER_BATCH_KD"); return e && e[0] == '1'; }();
     if (int rc = run_prep_sort(xyz1, b, n, X.scan, X.meta, X.boxes, st, X.perm, X.inv, walk, kd)) return rc;
     if (int rc = run_prep_sort(xyz2, b, m, Y.scan, Y.meta, Y.boxes, st, Y.perm, Y.inv, walk, kd)) return rc;
@@ -1268,8 +1269,14 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
     constexpr int NTB = 64;       // two warps per CTA, 512-candidate tiles: see nn_kernel
     if (walk) {
       p.bbX = block_boxes_of(X.boxes, b, n); p.bbY = block_boxes_of(Y.boxes, b, m);
-      const int tasks = (n + 63) / 64 + (m + 63) / 64 + 2;      // 64-row groups of both directions (+ the merged origin rows)
-      if (int rc = launch_walk<2, 8, false>(p, dim3((tasks + WALK_TPC - 1) / WALK_TPC, b, 1), st)) return rc;
+      static const bool walk_split = [] { const char* e = getenv("DUSTY_CHAMFER_WALK_SPLIT"); return !(e && e[0] == '0'); }();   // A/B
+      if (walk_split) {
+        const int tasks = (n + 31) / 32 + (m + 31) / 32 + 2;      // 32-row groups of both directions (+ the merged origin rows)
+        if (int rc = launch_walk_split<false>(p, dim3((tasks + WALK_TPC - 1) / WALK_TPC, b, 1), st)) return rc;
+      } else {
+        const int tasks = (n + 63) / 64 + (m + 63) / 64 + 2;      // 64-row groups
+        if (int rc = launch_walk<2, 8, false>(p, dim3((tasks + WALK_TPC - 1) / WALK_TPC, b, 1), st)) return rc;
+      }
     } else
     if (int rc = launch_nn<R, false, true, NTB, 512>(p, dim3((big + NTB * R - 1) / (NTB * R), b, 2), st)) return rc;
     unsort_kernel<<<(unsigned)(((long long)b * n + 255) / 256), 256, 0, st>>>(X.dist, X.idx, X.inv, b, n, p.strideX, dist1, idx1);
@@ -1419,7 +1426,8 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
     p.metaX = ma; p.metaY = mb;
     if (sorted) { p.boxX = ba; p.boxY = bb; p.bbX = block_boxes_of(ba, na, pa); p.bbY = symmetric ? p.bbX : block_boxes_of(bb, nb, pb); }
     // rows per lane, measured on 100 vs 100 un-sampled clouds: 1: 109.9 ms (1.7 % of the kept pairs visited), 2: 83.7 ms (2.3 %), 4: 85.9 ms (3.2 %)
-    if (walk) return launch_walk<2, 8, true>(p, grid, st);
+    static const bool walk_split = [] { const char* e = getenv("DUSTY_CHAMFER_WALK_SPLIT"); return !(e && e[0] == '0'); }();   // A/B
+    if (walk) return walk_split ? launch_walk_split<true>(p, grid, st) : launch_walk<2, 8, true>(p, grid, st);
     if (pair) {
       static const int pair_r = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
       // warps per CTA, measured on the 1000 vs 1000 x 2048 evaluation: 4: 466 ms, 6: 435, 8: 418, 10: 416, 12: 415 -- a plateau:

@@ -52,8 +52,8 @@ traffic = {}
 for d in kernels:
     name = d["Kernel Name"][0]
     key = ("chamfer_nn_pair_kernel_n1000" if "nn_pair" in name
-           else "chamfer_nn_walk_kernel_batch_8x32768" if "nn_walk_kernel<2, 8, 0" in name
-           else "chamfer_nn_walk_kernel_24x32768" if "nn_walk_kernel" in name
+           else "chamfer_nn_walk_kernel_batch_8x32768" if "nn_walk_kernel<2, 8, 0" in name or "nn_walk_split_kernel<0" in name
+           else "chamfer_nn_walk_kernel_24x32768" if "nn_walk" in name
            else "chamfer_nn_kernel_n1000" if "nn_kernel<8, 1, 0" in name or "nn_kernel<8, 1>" in name
            else "chamfer_nn_kernel_batch_sorted_8x32768" if "nn_kernel<4, 0, 1" in name
            else "chamfer_nn_kernel_merged_24x32768" if "nn_kernel" in name
