@@ -565,9 +565,13 @@ def main():
     # ---- end to end from pinned host buffers ----
     h_gen = gen.cpu().pin_memory(); h_ref = ref.cpu().pin_memory()
 
+    from dusty_gan_b200 import sharding
+
     def e2e_step():
-        g = h_gen.to(device, non_blocking=True); r = h_ref.to(device, non_blocking=True)
-        return M.compute_cov_mmd_1nna(g, r, 512, ("cd",), verbose=False)     # ends with the D2H of the scores
+        # one rank: a plain H2D copy; sharded: every rank uploads 1/G of the clouds and the ranks all-gather them over NVLink
+        # (each byte crosses PCIe once), then the evaluation -- which ends with the D2H of the scores
+        g = sharding.upload_sharded(h_gen, device); r = sharding.upload_sharded(h_ref, device)
+        return M.compute_cov_mmd_1nna(g, r, 512, ("cd",), verbose=False)
     e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -671,7 +675,8 @@ def main():
                    "parallelism": f"row-sharded x{world}, one all-gather of per-cloud (min, arg-min) keys ({24 * 2 * N} B per rank)" if world > 1 else "single GPU",
                    "l2": "256 MB buffer written between timed steps"},
         "e2e": {"value": e2e_value, "unit": "entries/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": int(h_gen.numel() + h_ref.numel()) * 4, "d2h_bytes_per_step": 28},
+                "h2d_bytes_per_step": int(h_gen.numel() + h_ref.numel()) * 4, "d2h_bytes_per_step": 28,
+                "h2d": "plain copy" if world == 1 else f"1/{world} of the clouds per rank over PCIe + one NVLink all-gather per set (bytes = all ranks together)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "scores": {k: scores[k] for k in ("mmd-cd", "cov-cd", "1-nn-accuracy-cd")},
     }

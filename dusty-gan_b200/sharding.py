@@ -90,6 +90,24 @@ def all_gather_keys(keys, group=None):
     return _all_gather_flat(keys.contiguous(), group).view(G, keys.numel())
 
 
+def upload_sharded(host, device, group=None):
+    """Host clouds (n, ...) -> the same tensor on ``device`` of every rank, each byte crossing PCIe once: rank r uploads
+    rows [r cap, (r+1) cap) and the ranks all-gather the blocks over NVLink (the optional pre-step:
+    what a data-parallel generation would hand to the evaluation). Every rank must pass the same host tensor. With one
+    rank it is a plain (non-blocking, if ``host`` is pinned) copy."""
+    _, G = world(group)
+    if G == 1:
+        return host.to(device, non_blocking=True)
+    rank, _ = world(group)
+    n = host.shape[0]
+    cap = rows_per_rank(n, G)
+    lo, hi = min(rank * cap, n), min((rank + 1) * cap, n)
+    mine = torch.zeros((cap,) + tuple(host.shape[1:]), device=device, dtype=host.dtype)
+    if hi > lo:
+        mine[: hi - lo].copy_(host[lo:hi], non_blocking=True)
+    return _all_gather_flat(mine, group).view((G * cap,) + tuple(host.shape[1:]))[:n]
+
+
 def symmetric_chamfer_matrix(clouds, group=None):
     """Full symmetric (n,n) Chamfer matrix of ``clouds`` (n,P,3); every rank returns the same tensor."""
     from .utils.metrics.cov_mmd_1nna import chamfer_matrix

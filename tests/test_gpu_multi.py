@@ -40,6 +40,9 @@ for (g, r), (scores1, mats1) in zip(cases, single):
     M.FUSED_EPILOGUE = True
     mats2 = M.pairwise_matrices(g, r)
     ok = ok and sharded == scores1 and unfused == scores1 and all(torch.equal(a, b) for a, b in zip(mats1, mats2))
+from dusty_gan_b200 import sharding          # sharded upload: 1/G of the clouds per rank over PCIe, one all-gather
+host = cases[2][0].cpu().pin_memory()
+ok = ok and torch.equal(sharding.upload_sharded(host, torch.device("cuda", dev)), cases[2][0])
 flags = [None] * dist.get_world_size(); dist.all_gather_object(flags, bool(ok))
 if rank == 0: print("RESULT", json.dumps({"ok": all(flags), "world": dist.get_world_size(), "backend": backend}))
 dist.destroy_process_group()

@@ -82,6 +82,9 @@ def _worker(rank, world, port, n, P, ret):
                 ok = ok and got[key] == want[key + "-cd"]
             for key in ("tp", "fp", "fn", "tn"):
                 ok = ok and got[key] == want["1-nn-" + key + "-cd"]
+        # ---- sharded upload: every rank ends up with the full tensor, rows in order, for n not divisible by the world ----
+        host = torch.from_numpy(clouds)
+        ok = ok and torch.equal(sharding.upload_sharded(host, torch.device("cpu")), host)
         flags = [None] * world
         dist.all_gather_object(flags, ok)
         if rank == 0:
