@@ -783,22 +783,37 @@ __device__ __forceinline__ float ordered_float(unsigned u) {
 constexpr int KD_MAXSEG = SORT_CAP / 64;
 // NT threads per CTA: 1024 for large clouds (one CTA per SM: the keys take up to 128 KB), 256 for clouds of at most 4096
 // points, where several CTAs per SM hide the latency of the per-level passes (2000 clouds of 2048 points: 1.17 -> 0.72 ms)
+// One launch sorts the clouds of up to two sets (the X and Y sides of a call: CTAs [0, clouds0) take side 0, the others side 1),
+// so that the two sides of a small batch share the GPU instead of running one after the other.
+struct SortSide {
+  const float* xyz; int count; long long stride; float4* out; int2* meta; float4* boxes; int boxstride;
+  int* perm; int* inv; float4* block_boxes;
+};
+struct SortArgs { SortSide s[2]; int clouds0; };
+
 template <bool KD, int NT>
-__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) prep_sort_kernel(const float* __restrict__ xyz, int count, long long stride,
-                                                             float4* __restrict__ out, int2* __restrict__ meta,
-                                                             float4* __restrict__ boxes, int boxstride,
-                                                             int* __restrict__ perm_all, int* __restrict__ inv_all,
-                                                             float4* __restrict__ block_boxes) {
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) prep_sort_kernel(const SortArgs a) {
   extern __shared__ unsigned keys[];            // n2 keys (next power of two >= count)
   __shared__ float red[NT / 32][6];
   __shared__ int wsum[NT / 32];
   __shared__ int first_zero;
+  const bool side = (int)blockIdx.x >= a.clouds0;
+  const long long c = (int)blockIdx.x - (side ? a.clouds0 : 0);
+  const float* __restrict__ const xyz = side ? a.s[1].xyz : a.s[0].xyz;
+  const int count = side ? a.s[1].count : a.s[0].count;
+  const long long stride = side ? a.s[1].stride : a.s[0].stride;
+  float4* __restrict__ const out = side ? a.s[1].out : a.s[0].out;
+  int2* __restrict__ const meta = side ? a.s[1].meta : a.s[0].meta;
+  float4* __restrict__ const boxes = side ? a.s[1].boxes : a.s[0].boxes;
+  const int boxstride = side ? a.s[1].boxstride : a.s[0].boxstride;
+  int* __restrict__ const perm_all = side ? a.s[1].perm : a.s[0].perm;
+  int* __restrict__ const inv_all = side ? a.s[1].inv : a.s[0].inv;
+  float4* __restrict__ const block_boxes = side ? a.s[1].block_boxes : a.s[0].block_boxes;
   // batch front end only: perm[position] = original index (the merged origin point stands for the FIRST zero point,
   // the arg-min the reference reports among equal distances), inv[original index] = position
-  int* const perm = perm_all ? perm_all + blockIdx.x * stride : nullptr;
-  int* const inv = inv_all ? inv_all + (long long)blockIdx.x * count : nullptr;
+  int* const perm = perm_all ? perm_all + c * stride : nullptr;
+  int* const inv = inv_all ? inv_all + c * count : nullptr;
   if (threadIdx.x == 0) first_zero = 0x7fffffff;
-  const long long c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* src = xyz + c * count * 3;
   float* dst = reinterpret_cast<float*>(out + c * stride);
@@ -1144,34 +1159,47 @@ __global__ void __launch_bounds__(256) unsort_kernel(const float* __restrict__ d
   if (idx) idx[g] = idx_sorted[o];
 }
 
+static SortSide sort_side(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, int* perm, int* inv,
+                          bool walkable) {
+  return SortSide{xyz, count, (long long)padded_of(count), out, meta, boxes, padded_of(count) / CHUNK * 2, perm, inv,
+                  walkable ? block_boxes_of(boxes, clouds, count) : nullptr};
+}
+
 template <bool KD, int NT>
-static int launch_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st,
-                            int* perm, int* inv, bool walkable) {
+static int launch_prep_sort(const SortArgs& a, long long clouds, int maxcount, cudaStream_t st) {
   int n2 = 1;
-  while (n2 < count) n2 <<= 1;
+  while (n2 < maxcount) n2 <<= 1;
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
     DUSTY_CUDA(cudaFuncSetAttribute(prep_sort_kernel<KD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 4));
     configured[dev] = true;
   }
-  prep_sort_kernel<KD, NT><<<(unsigned)clouds, NT, (size_t)n2 * 4, st>>>(xyz, count, padded_of(count), out, meta, boxes,
-                                                                            padded_of(count) / CHUNK * 2, perm, inv,
-                                                                            walkable ? block_boxes_of(boxes, clouds, count) : nullptr);
+  prep_sort_kernel<KD, NT><<<(unsigned)clouds, NT, (size_t)n2 * 4, st>>>(a);
   DUSTY_AFTER_LAUNCH(KD ? "chamfer prep_sort_kernel<kd>" : "chamfer prep_sort_kernel");
   return 0;
 }
 
+// walkable: for the pair / walk kernels (block boxes, origin kept out of its chunk's box); kd: k-d order (Morton otherwise).
+// clouds1 > 0: a second set in the same launch.
+static int run_prep_sort2(const SortSide& s0, long long clouds0, const SortSide& s1, long long clouds1, cudaStream_t st, bool walkable,
+                          bool kd) {
+  if (clouds0 + clouds1 == 0) return 0;
+  if (clouds0 + clouds1 > 0x7fffffffLL) return fail_arg(DUSTY_EINVAL, "chamfer: too many clouds in one sort launch");
+  SortArgs a{};
+  a.s[0] = s0; a.s[1] = clouds1 > 0 ? s1 : s0; a.clouds0 = (int)clouds0;
+  const int maxcount = clouds1 > 0 && s1.count > s0.count ? s1.count : s0.count;
+  static const bool small_ctas = [] { const char* e = getenv("DUSTY_CHAMFER_SORT_SMALL"); return !(e && e[0] == '0'); }();   // A/B
+  const long long clouds = clouds0 + clouds1;
+  if (maxcount <= 4096 && small_ctas)
+    return walkable && kd ? launch_prep_sort<true, 256>(a, clouds, maxcount, st) : launch_prep_sort<false, 256>(a, clouds, maxcount, st);
+  return walkable && kd ? launch_prep_sort<true, SORT_TPB>(a, clouds, maxcount, st) : launch_prep_sort<false, SORT_TPB>(a, clouds, maxcount, st);
+}
+
 static int run_prep_sort(const float* xyz, long long clouds, int count, float4* out, int2* meta, float4* boxes, cudaStream_t st,
                          int* perm = nullptr, int* inv = nullptr, bool walkable = false, bool kd = true) {
-  // walkable: for nn_pair_kernel / nn_walk_kernel (block boxes, origin kept out of its chunk's box); kd: k-d order (Morton otherwise)
-  if (clouds == 0) return 0;
-  static const bool small_ctas = [] { const char* e = getenv("DUSTY_CHAMFER_SORT_SMALL"); return !(e && e[0] == '0'); }();   // A/B
-  if (count <= 4096 && small_ctas)
-    return walkable && kd ? launch_prep_sort<true, 256>(xyz, clouds, count, out, meta, boxes, st, perm, inv, walkable)
-                          : launch_prep_sort<false, 256>(xyz, clouds, count, out, meta, boxes, st, perm, inv, walkable);
-  return walkable && kd ? launch_prep_sort<true, SORT_TPB>(xyz, clouds, count, out, meta, boxes, st, perm, inv, walkable)
-                        : launch_prep_sort<false, SORT_TPB>(xyz, clouds, count, out, meta, boxes, st, perm, inv, walkable);
+  const SortSide s0 = sort_side(xyz, clouds, count, out, meta, boxes, perm, inv, walkable);
+  return run_prep_sort2(s0, clouds, s0, 0, st, walkable, kd);
 }
 
 #include "chamfer_pair.cuh"
@@ -1254,8 +1282,8 @@ extern "C" int dusty_chamfer_forward(const float* xyz1, const float* xyz2, int b
     // searched 2 N times, takes the k-d order. DUSTY_CHAMFER_BATCH_KD=1 for A/B runs. (With the split walk kernel -- 32-row groups,
     // four times the CTAs -- Morton + walk is 0.78 / 1.04 / 2.02 ms.)
     static const bool kd = [] { const char* e = getenv("DUSTY_CHAMFER_BATCH_KD"); return e && e[0] == '1'; }();
-    if (int rc = run_prep_sort(xyz1, b, n, X.scan, X.meta, X.boxes, st, X.perm, X.inv, walk, kd)) return rc;
-    if (int rc = run_prep_sort(xyz2, b, m, Y.scan, Y.meta, Y.boxes, st, Y.perm, Y.inv, walk, kd)) return rc;
+    if (int rc = run_prep_sort2(sort_side(xyz1, b, n, X.scan, X.meta, X.boxes, X.perm, X.inv, walk), b,
+                                sort_side(xyz2, b, m, Y.scan, Y.meta, Y.boxes, Y.perm, Y.inv, walk), b, st, walk, kd)) return rc;
     Params p{};
     p.scanX = X.scan; p.scanY = Y.scan;
     p.countX = n; p.countY = m;
@@ -1399,8 +1427,9 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
   const bool walk = sorted && !pair && walk_enabled;
   if (!prepared) {
     if (sorted) {
-      if (int rc = run_prep_sort(A, na, pa, sa, ma, ba, st, nullptr, nullptr, pair || walk)) return rc;
-      if (!symmetric) if (int rc = run_prep_sort(B, nb, pb, sb, mb, bb, st, nullptr, nullptr, pair || walk)) return rc;
+      const bool wk = pair || walk;
+      if (int rc = run_prep_sort2(sort_side(A, na, pa, sa, ma, ba, nullptr, nullptr, wk), na,
+                                  sort_side(B, nb, pb, sb, mb, bb, nullptr, nullptr, wk), symmetric ? 0 : nb, st, wk, true)) return rc;
     } else if (merge) {
       if (int rc = run_prep_merge(A, na, pa, sa, ma, st)) return rc;
       if (!symmetric) if (int rc = run_prep_merge(B, nb, pb, sb, mb, st)) return rc;
