@@ -1458,15 +1458,12 @@ static int matrix_impl(const float* A, int na, int pa, const float* B, int nb, i
     static const bool walk_split = [] { const char* e = getenv("DUSTY_CHAMFER_WALK_SPLIT"); return !(e && e[0] == '0'); }();   // A/B
     if (walk) return walk_split ? launch_walk_split<true>(p, grid, st) : launch_walk<2, 8, true>(p, grid, st);
     if (pair) {
-      static const int pair_r = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
-      // warps per CTA, measured on the 1000 vs 1000 x 2048 evaluation: 4: 466 ms, 6: 435, 8: 418, 10: 416, 12: 415 -- a plateau:
-      // the kernel is bound by issue slots and FFMA2/FMNMX3 dispatch, not by latency
+      // Measured on the 1000 vs 1000 x 2048 evaluation (64-row groups, nn_pair_kernel<R, SUB, NW>): rows per lane R = 1 / 2 / 4:
+      // 444 / 418 / 536 ms; candidates per search window SUB = 8 / 16 / 32: 419 / 436 / 512 ms; warps per CTA NW = 4 / 6 / 8 / 10 / 12:
+      // 466 / 435 / 418 / 416 / 415 ms (a plateau: bound by issue slots and FFMA2/FMNMX3 dispatch, not by latency). The split
+      // kernel's 32-row groups: 392 ms. Only the two best shapes are instantiated.
       static const bool pair_split = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_SPLIT"); return !(e && e[0] == '0'); }();
-      if (pair_split) return launch_pair_split(p, grid, st);
-      static const int pair_sub = [] { const char* e = getenv("DUSTY_CHAMFER_PAIR_SUB"); const int v = e ? atoi(e) : 8; return v == 16 || v == 32 ? v : 8; }();
-      if (pair_sub == 16) return pair_r == 4 ? launch_pair<4, 16>(p, grid, st) : launch_pair<2, 16>(p, grid, st);
-      if (pair_sub == 32) return launch_pair<2, 32>(p, grid, st);
-      return pair_r == 1 ? launch_pair<1, 8>(p, grid, st) : pair_r == 4 ? launch_pair<4, 8>(p, grid, st) : launch_pair<2, 8>(p, grid, st);
+      return pair_split ? launch_pair_split(p, grid, st) : launch_pair<2, 8>(p, grid, st);
     }
     static const bool narrow = [] { const char* e = getenv("DUSTY_CHAMFER_NARROW"); return !(e && e[0] == '0'); }();   // A/B switch
     if (sorted && merged_r == 4 && narrow) {
