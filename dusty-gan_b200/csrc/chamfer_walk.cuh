@@ -6,9 +6,10 @@
 //     tree; at most 32 blocks, their boxes come from prep_sort_kernel) and the warp opens blocks best first; inside
 //     an open block a lane bounds one chunk and the warp scans chunks best first. Both levels stop at the first
 //     bound beyond the largest running minimum of the warp's 64 rows;
-//   * candidates, boxes and rows are read from global memory through L1 (the kernel uses almost no shared memory,
+//   * candidates, boxes and rows are read from global memory through L1 (the kernel uses little shared memory,
 //     so L1 keeps ~200 KB): row groups are taken in k-d order, so the warps of a CTA work on neighbouring groups and
-//     walk overlapping chunks.
+//     walk overlapping chunks. (The split variant below -- the default -- stages the chunk it scans through 512 bytes
+//     of per-warp shared memory: a half-warp-uniform LDG.128 costs far more L1 wavefronts than the same LDS.128.)
 // nn_kernel<4,1,1,64,512> streams every tile of the candidate cloud past every row block (33 MB of L2 -> shared
 // memory traffic per entry at 16 k points, tiles visited in storage order); the walk reads the chunks it scans.
 // MATRIX: one CTA per matrix entry, per-task sums added in task order (deterministic under the dynamic task
