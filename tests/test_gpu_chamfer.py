@@ -281,3 +281,26 @@ def test_forward_against_reference_cuda_golden(golden):
         d1, d2, i1, i2 = run_forward(a, c)
         for d, r, ix, k in ((d1, g[f"cd{i}_dist1"], i1, g[f"cd{i}_idx1"]), (d2, g[f"cd{i}_dist2"], i2, g[f"cd{i}_idx2"])):
             assert np.array_equal(d, r) and np.array_equal(ix, k)      # the reference kernel's own output on a B200
+
+
+@pytest.mark.parametrize("P,merge", [(700, True), (3000, True), (700, False)])
+def test_matrix_prepared_flag_reuses_the_scan_copies(P, merge):
+    """DUSTY_MATRIX_PREPARED: a second call on the same workspace skips the scan-format / k-d preparation of the clouds
+    (resident-pair kernel at 700 points, walk kernel at 3000, brute-force kernel without the merge flag)."""
+    from dusty_gan_b200 import _lib
+    from dusty_gan_b200.utils.metrics.cov_mmd_1nna import chamfer_matrix
+    a, b = cuda(lidar_like_clouds(5, P, 901, dropped=0.3)), cuda(lidar_like_clouds(4, P, 902, dropped=0.3))
+    lib = _lib.load()
+    flags = _lib.MATRIX_MERGE_ORIGIN if merge else 0
+    nbytes = lib.dusty_chamfer_matrix_workspace_bytes(5, P, 4, P)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    M = torch.zeros(5, 4, device="cuda")
+    launches = _lib.launch_count()
+    _lib.check(lib.dusty_chamfer_matrix(_lib.ptr(a), 5, P, _lib.ptr(b), 4, P, 0, 2, 1, flags, _lib.ptr(M), 4, _lib.ptr(ws), nbytes,
+                                        _lib.stream_of(a)), "first")
+    first = _lib.launch_count() - launches
+    _lib.check(lib.dusty_chamfer_matrix(_lib.ptr(a), 5, P, _lib.ptr(b), 4, P, 2, 5, 1, flags | _lib.MATRIX_PREPARED, _lib.ptr(M), 4,
+                                        _lib.ptr(ws), nbytes, _lib.stream_of(a)), "second")
+    assert _lib.launch_count() - launches - first == 1 and first >= 2      # the second call is the search kernel alone
+    torch.cuda.synchronize()
+    assert torch.equal(M, chamfer_matrix(a, b, merge_origin=merge))
